@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — scan-matches/sec of the PSO/NDT hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+A step = one pass of the hot path (pso_optimization, 70 particles x 50 iterations, 1081-beam scan
+vs 50 m / 0.5 m NDT map) over a batch of B independent scan-match problems per GPU, each carrying
+its own dense (mu, Sigma^-1, built) table.
+
+  value      whole-job matches/s with the batch resident in HBM (dense tables, points, guesses):
+             K0 table compaction + K1 rand() stream + K2 PSO, CUDA events on the launch stream
+  e2e        the same metric through ndtpso_align_batch with HOST buffers (pinned): H2D of every
+             input + kernels + D2H of the poses inside the timed region
+  roofline   dominant kernel (pso_kernel): algorithmic bytes / its event-timed duration vs the
+             measured HBM peak; the fp64 pipe fraction beside it (the bound that really binds)
+  cpu_baseline  the reference's own CPU path (oracle/_ref if present, else the oracle port) on
+             this box's host cores, bounded sample
+
+`--impl reference` times only the CPU arm, same metric/config.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scan-matches/sec (1081-pt scan, 70 particles x 50 iters)"
+P, I = 70, 50
+ALG_BYTES_PER_MATCH = 16 * 1081 + 49 * 10000 + 80          # 507 376 B
+ALG_FLOP_PER_MATCH = 31 * (P + 1 + P * I) * 1081 + 17 * P * I  # ~119.7 MFLOP
+
+
+# ------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------
+def make_problems(batch, rank):
+    """`batch` cfg2-shaped problems for this rank, every one with its own table arrays."""
+    from ndtpso_slam_b200 import workload
+    return workload.cfg2_batch(batch, first=rank * batch)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, scan_args, seeds = args
+    from ndtpso_slam_b200 import synthetic as syn
+    from oracle import binding
+    ss = syn.trajectory_problem(syn.CFG2, scan_args)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        R = binding.Reference()
+        rf, q = R.build_problem(ss)
+        rf.build()
+        t0 = time.perf_counter()
+        for s in seeds:
+            R.pso(rf, q, ss.guess, ss.deviation, P, I, seed=s, num_threads=1)
+    else:
+        from ndtpso_slam_b200 import workload
+        flat = workload.cfg2_batch(1, first=scan_args)[0]
+        O = binding.Oracle()
+        t0 = time.perf_counter()
+        for s in seeds:
+            O.pso(flat, flat["guess"], flat["deviation"], P, I, seed=s)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(matches_per_worker):
+    """matches/s of the reference CPU path using every host core: nproc single-thread workers over
+    disjoint problems (its deterministic mode; in-process outer parallelism is impossible because
+    the reference draws from the process-global rand()).  Also times the as-shipped OpenMP mode."""
+    from oracle import binding
+    kind = "reference" if os.path.exists(binding.REF_SO) else "port"
+    if kind == "port":
+        binding.build()
+    cores = os.cpu_count() or 1
+    jobs = [(kind, w, list(range(1 + w * 1000, 1 + w * 1000 + matches_per_worker))) for w in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    # wall includes process start-up and map building; use the slowest worker's solve time instead
+    with mp.get_context("spawn").Pool(cores) as pool:
+        per = pool.map(_cpu_worker, jobs)
+    rate = cores * matches_per_worker / max(per)
+    out = {"value": rate, "unit": "scan-matches/s", "cores": cores, "kind": kind,
+           "sample": f"{cores} single-thread workers x {matches_per_worker} cfg2 matches each (70x50, 1081 pts), slowest worker {max(per):.2f} s",
+           "single_thread_ms_per_match": 1e3 * float(np.median(per)) / matches_per_worker}
+    if kind == "reference":
+        from ndtpso_slam_b200 import synthetic as syn
+        R = binding.Reference()
+        ss = syn.trajectory_problem(syn.CFG2, 0)
+        rf, q = R.build_problem(ss)
+        ts = [R.pso(rf, q, ss.guess, ss.deviation, P, I, seed=s, num_threads=-1)[1] for s in range(1, 9)]
+        out["as_shipped_openmp"] = {"value": 1.0 / float(np.median(ts[2:])), "unit": "scan-matches/s", "threads": R.lib.ref_omp_max_threads(),
+                                    "note": "num_threads=-1 inside one match; non-deterministic result (SURVEY.md section 0.5)"}
+    return out, wall
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(1, args.ref_matches)
+    rates = []
+    base = None
+    t_all = time.perf_counter()
+    for step in range(args.warmup + args.steps):
+        base, _ = cpu_reference_rate(per_step)
+        if step >= args.warmup:
+            rates.append(base["value"])
+        if time.perf_counter() - t_all > 240:
+            break
+    value = float(np.mean(rates)) if rates else base["value"]
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": args.gpus, "steps": len(rates),
+            "warmup": args.warmup, "ms_per_step": 1e3 * base["cores"] * per_step / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 (configs[1] shape): 1081-beam scan vs 50 m/0.5 m NDT map, 70 particles x 50 iterations; "
+                                   "bounded sample on the host cores", "particles": P, "iterations": I},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "scan-matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from ndtpso_slam_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+
+    flats = make_problems(B, rank)
+    ctx = capi.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    conf = capi.PsoConfig.make(population=P, iterations=I)
+
+    # pinned host copies of every input array (the e2e path copies from these every step)
+    pinned_flats, h2d_bytes = [], 0
+    for f in flats:
+        g = dict(f)
+        for k in ("points", "mean", "inv_cov", "built"):
+            t = torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory()
+            g[k] = t.numpy()
+            g["_keep_" + k] = t
+            h2d_bytes += t.numel() * t.element_size()
+        pinned_flats.append(g)
+    pset = capi.ProblemSet(pinned_flats)
+    h2d_bytes += B * (48 + 4)  # guess, deviation, seed
+    d2h_bytes = B * 32
+
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(world * B * 4, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident arm: value
+    bt = ctx.batch(pset, conf)
+    res_ptr = bt.device_results_ptr()
+    res_t = None
+    if world > 1:
+        # view the library's result buffer as a tensor for the NCCL all-gather of the solved poses
+        class _Ext:
+            __cuda_array_interface__ = {"shape": (B * 4,), "typestr": "<f8", "data": (res_ptr, False), "version": 3}
+        res_t = torch.as_tensor(_Ext(), device="cuda")
+
+    def resident_step():
+        bt.solve()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res_t)
+
+    for _ in range(args.warmup):
+        l2_flush.fill_(1)
+        resident_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k2_ms = []
+    barrier()
+    for k in range(args.steps):
+        l2_flush.fill_(k & 0xFF)  # flush L2 between timed iterations (not timed)
+        ev[k][0].record(stream)
+        resident_step()
+        ev[k][1].record(stream)
+        k2_ms.append(None)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kt = bt.kernel_times_ms()  # last solve: K0, K1, K2
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    pose, cost = bt.results()
+    stats = bt.stats()
+
+    # ---- e2e arm: host buffers in, host poses out, every step
+    for _ in range(max(1, args.warmup // 2)):
+        ctx.align_batch(pset, conf)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ep, ec = ctx.align_batch(pset, conf)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop()
+    assert np.array_equal(ep, pose), "e2e and resident paths disagree"
+
+    fp64_peak = ctx.fp64_peak_tflops()
+    bt.close()
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        value = world * B * args.steps / (total_ms * 1e-3)
+        e2e = world * B * args.steps / e2e_s
+        k2_s = float(kt[2]) * 1e-3
+        ach_gbs = ALG_BYTES_PER_MATCH * B / k2_s / 1e9
+        ach_tf = ALG_FLOP_PER_MATCH * B / k2_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cfg2 shape (configs[1]; batched as configs[2]): {B} independent 1081-beam scan-matches per GPU vs "
+                                   "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations",
+                       "batch_per_gpu": B, "particles": P, "iterations": I, "l2": "flushed between timed iterations (256 MiB write)",
+                       "collective": "NCCL all-gather of [B][4] fp64 poses per step" if world > 1 else "none"},
+            "e2e": {"value": e2e, "unit": "scan-matches/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "pso_kernel", "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": {"compact_map": float(kt[0]), "rng_fill": float(kt[1]), "pso": float(kt[2])},
+                         "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                                  "note": "algorithmic flops (31/point-eval); peak = DFMA probe on this GPU; this is the bound that binds"}},
+            "rounds_per_match": float(stats[:, 0].mean()), "pose0": [float(v) for v in pose[0]],
+        }
+        if not args.no_cpu:
+            line["cpu_baseline"], _ = cpu_reference_rate(args.ref_matches)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="scan-match problems per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-matches", type=int, default=4, help="CPU arm: matches per host worker per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

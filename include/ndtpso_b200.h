@@ -1,0 +1,163 @@
+/* ndtpso_b200.h — C ABI of the B200-native PSO/NDT scan-matching hot path.
+ *
+ * This is the drop-in boundary for libndtpso_slam's scan matcher.  The reference has
+ * no plugin mechanism; the seam is link-time: its ROS node calls
+ *     current_pose_ = ref_frame_->align(previous_pose_, current_frame_);
+ *                                   (src/ndtpso_slam_node.cpp:194)
+ * and NDTFrame::align (lib/ndtpso_slam/ndtframe.cpp:251-266) calls
+ *     pso_optimization(guess, this, new_frame, deviation)         (ndtframe.cpp:257)
+ * declared at include/ndtpso_slam/core.h:16-19, which evaluates
+ *     cost_function(trans, ref_frame, new_frame)                   (core.h:49-50)
+ * P+1+P*I times.  The entry points below are what a C/C++/ctypes binding for that path
+ * binds: plain pointers and sizes, no Eigen, STL or torch types.  INTEGRATION.md shows
+ * the few lines a maintainer adds to lib/ndtpso_slam/core.cpp to route through them.
+ *
+ * All floating point is IEEE fp64, as in the reference.  Every function returns an int
+ * status (0 = NDTPSO_OK, negative = error) and never throws or aborts; the reference
+ * path itself cannot fail, so a caller may treat any non-zero
+ * status as fatal.  There is NO CPU fallback behind this ABI: without a CUDA device
+ * ndtpso_ctx_create fails with NDTPSO_ERR_NODEVICE.
+ *
+ * Threading: one in-flight call per context; contexts are independent (one per GPU).
+ */
+#ifndef NDTPSO_B200_H
+#define NDTPSO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDTPSO_ABI_VERSION 1
+
+enum {
+  NDTPSO_OK = 0,
+  NDTPSO_ERR_ARG = -1,      /* null pointer, negative size, unsupported configuration */
+  NDTPSO_ERR_CUDA = -2,     /* a CUDA runtime call or kernel failed; see ndtpso_last_error */
+  NDTPSO_ERR_NOMEM = -3,    /* host or device allocation failed */
+  NDTPSO_ERR_NODEVICE = -4, /* no usable CUDA device (the product has no CPU path) */
+  NDTPSO_ERR_LIMIT = -5     /* population too large for one CTA's shared memory */
+};
+
+typedef struct ndtpso_ctx ndtpso_ctx;     /* one GPU, one stream, cached device/pinned arenas */
+typedef struct ndtpso_batch ndtpso_batch; /* a batch of problems resident in HBM */
+
+/* Mirror of `struct PSOConfig` (include/ndtpso_slam/config.h:27-38), field for field.
+ * num_threads is accepted and ignored: the device path is deterministic and equals the
+ * reference run with num_threads = 1 (its OpenMP mode is racy). */
+typedef struct ndtpso_pso_config {
+  int32_t iterations;   /* PSOConfig::iterations      default 50  (PSO_ITERATIONS) */
+  int32_t population;   /* PSOConfig::populationSize  default 30  (PSO_POPULATION_SIZE) */
+  int32_t num_threads;  /* PSOConfig::num_threads     default -1 */
+  int32_t reserved;     /* must be 0 */
+  double w;             /* coeff.w          default .8 */
+  double c1;            /* coeff.c1         default 2. */
+  double c2;            /* coeff.c2         default 2. */
+  double w_dumping;     /* coeff.w_dumping  default 1. */
+} ndtpso_pso_config;
+
+/* Fills *conf with the reference defaults (what 2-argument NDTFrame::align() runs). */
+void ndtpso_pso_config_default(ndtpso_pso_config* conf);
+
+/* Read-only view of the reference frame's NDT table: exactly the fields cost_function
+ * reads through NDTFrame::getCellIndex (ndtframe.cpp:240-249) and
+ * NDTCell::normalDistribution (ndtcell.cpp:70-78).  Cell index = ix + w_cells*iy.
+ *
+ *   dense  form (n_sparse <  0): mean/inv_cov/built have w_cells*h_cells rows, row i = cell i;
+ *   sparse form (n_sparse >= 0): mean/inv_cov have n_sparse rows, row r belongs to cell
+ *                                cell_index[r] (strictly ascending), every listed cell is
+ *                                built, every other cell is not; `built` is ignored.
+ */
+typedef struct ndtpso_map_view {
+  int32_t w_cells;       /* NDTFrame::widthNumOfCells  (ndtframe.cpp:27) */
+  int32_t h_cells;       /* NDTFrame::heightNumOfCells (ndtframe.cpp:28) */
+  double width_m;        /* NDTFrame::width  (uint16 metres, ndtframe.h:32) */
+  double height_m;       /* NDTFrame::height */
+  double cell_side;      /* NDTFrame::cell_side */
+  double x_min, x_max;   /* NDTFrame::s_x_min, s_x_max (ndtframe.cpp:57-58) */
+  double y_min, y_max;   /* NDTFrame::s_y_min, s_y_max (ndtframe.cpp:64-65) */
+  const double* mean;    /* [rows][2]  NDTCell::mean        (ndtcell.h:73) */
+  const double* inv_cov; /* [rows][4]  NDTCell::s_inv_covar (ndtcell.h:66), row-major 00,01,10,11 */
+  const uint8_t* built;  /* [w_cells*h_cells] NDTCell::built (ndtcell.h:76); dense form only */
+  int32_t n_sparse;      /* < 0: dense form */
+  int32_t reserved;      /* must be 0 */
+  const int32_t* cell_index; /* [n_sparse], sparse form only */
+} ndtpso_map_view;
+
+/* One scan-match problem = one pso_optimization call (core.cpp:50-116). */
+typedef struct ndtpso_problem {
+  ndtpso_map_view map;      /* `ref_frame`; problems may share a table (same pointers) */
+  const double* points_xy;  /* [n_points][2]: new_frame->cells[*].points_vector[0] in the
+                               iteration order of core.cpp:33-36 */
+  int32_t n_points;
+  uint32_t seed;            /* used when rand_stream == NULL: the random numbers are those of
+                               glibc srand(seed); rand(); rand(); ... */
+  double guess[3];          /* initial_guess (x, y, theta) */
+  double deviation[3];      /* deviation (core.h:18) */
+  const int32_t* rand_stream; /* NULL, or rand_count raw std::rand() outputs drawn by the host
+                               in call order (drop-in mode: keeps the process-global stream
+                               in lock-step with the CPU build) */
+  int64_t rand_count;       /* >= ndtpso_rand_draws(conf) when rand_stream != NULL */
+} ndtpso_problem;
+
+/* ---- context ------------------------------------------------------------------- */
+int ndtpso_abi_version(void);
+int ndtpso_device_count(void);
+int ndtpso_ctx_create(int device, ndtpso_ctx** out);
+void ndtpso_ctx_destroy(ndtpso_ctx* ctx);
+/* Launch on `cuda_stream` (a cudaStream_t) instead of the context's own stream. */
+int ndtpso_ctx_set_stream(ndtpso_ctx* ctx, void* cuda_stream);
+const char* ndtpso_last_error(const ndtpso_ctx* ctx);
+
+enum {
+  NDTPSO_OPT_WARPS_PER_CTA = 1, /* 0 = auto */
+  NDTPSO_OPT_SMEM_BYTES = 2,    /* dynamic shared memory per CTA; 0 = auto */
+  NDTPSO_OPT_CLUSTER = 3        /* CTAs cooperating on one problem; 0 = auto */
+};
+int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value);
+
+/* Number of std::rand() calls one pso_optimization makes: 3 + 3P + 6PI (core.cpp:14,58-69,84). */
+int64_t ndtpso_rand_draws(const ndtpso_pso_config* conf);
+
+/* ---- the hot path --------------------------------------------------------------- */
+
+/* Replaces pso_optimization (core.h:16-19) for n independent problems: host buffers in,
+ * host buffers out.  out_pose[b] = global_best.best_position, out_cost[b] =
+ * global_best.best_cost (the reference only prints it, core.cpp:111-114). out_cost may be NULL. */
+int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf,
+                       double* out_pose /* [n][3] */, double* out_cost /* [n] */);
+
+/* Replaces cost_function (core.h:49-50): cost of `n_poses` candidate poses per problem. */
+int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int32_t n_poses,
+                      const double* poses /* [n][n_poses][3] */, double* out_cost /* [n][n_poses] */);
+
+/* ---- the same path with the batch kept resident in HBM -------------------------- */
+/* upload (H2D, asynchronous on the context's stream) */
+int ndtpso_batch_create(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf,
+                        ndtpso_batch** out);
+/* enqueue the kernels; asynchronous; may be called repeatedly (each call re-solves from scratch) */
+int ndtpso_batch_solve(ndtpso_batch* batch);
+/* device pointer to [n][4] fp64 = (x, y, theta, cost) per problem, valid after solve completes */
+void* ndtpso_batch_device_results(ndtpso_batch* batch);
+/* D2H + synchronise; either output may be NULL */
+int ndtpso_batch_results(ndtpso_batch* batch, double* out_pose /* [n][3] */, double* out_cost /* [n] */);
+/* per-problem counters after a solve: out[b] = {rounds, gbest_updates} */
+int ndtpso_batch_stats(ndtpso_batch* batch, int32_t* out /* [n][2] */);
+/* device time of the last solve's kernels in ms, measured with CUDA events on the launch stream:
+ * out_ms = {table compaction (K0), rand() stream (K1), PSO (K2)}; synchronises on the solve */
+int ndtpso_batch_kernel_times(ndtpso_batch* batch, double* out_ms /* [3] */);
+void ndtpso_batch_destroy(ndtpso_batch* batch);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t ndtpso_ctx_launch_count(const ndtpso_ctx* ctx);
+int ndtpso_ctx_synchronize(ndtpso_ctx* ctx);
+
+/* ---- device self-measurement (roofline denominators MEASURED_PEAKS.json lacks) --- */
+/* Sustained fp64 FMA throughput of this GPU in TFLOP/s (2 flop per DFMA). */
+int ndtpso_measure_fp64_peak(ndtpso_ctx* ctx, double* out_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDTPSO_B200_H */

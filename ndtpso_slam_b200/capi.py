@@ -1,0 +1,262 @@
+"""ctypes binding of include/ndtpso_b200.h (libndtpso_b200.so).
+
+This is the host-side mirror used by tests/, bench.py and smoke(): every call goes through
+the C ABI, exactly as a C++ caller would.  There is no fallback: if the library is missing
+or no CUDA device is present, `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_LIMIT = 0, -1, -2, -3, -4, -5
+OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER = 1, 2, 3
+
+#: every symbol include/ndtpso_b200.h declares
+EXPORTS = [
+    "ndtpso_abi_version", "ndtpso_pso_config_default", "ndtpso_device_count", "ndtpso_ctx_create", "ndtpso_ctx_destroy",
+    "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch",
+    "ndtpso_cost_batch", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
+    "ndtpso_batch_stats", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
+]
+
+
+class PsoConfig(C.Structure):
+    """struct ndtpso_pso_config == reference PSOConfig (include/ndtpso_slam/config.h:27-38)."""
+    _fields_ = [("iterations", C.c_int32), ("population", C.c_int32), ("num_threads", C.c_int32), ("reserved", C.c_int32),
+                ("w", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("w_dumping", C.c_double)]
+
+    @classmethod
+    def make(cls, population=30, iterations=50, w=0.8, c1=2.0, c2=2.0, w_dumping=1.0):
+        return cls(int(iterations), int(population), -1, 0, w, c1, c2, w_dumping)
+
+
+class MapView(C.Structure):
+    _fields_ = [("w_cells", C.c_int32), ("h_cells", C.c_int32),
+                ("width_m", C.c_double), ("height_m", C.c_double), ("cell_side", C.c_double),
+                ("x_min", C.c_double), ("x_max", C.c_double), ("y_min", C.c_double), ("y_max", C.c_double),
+                ("mean", C.c_void_p), ("inv_cov", C.c_void_p), ("built", C.c_void_p),
+                ("n_sparse", C.c_int32), ("reserved", C.c_int32), ("cell_index", C.c_void_p)]
+
+
+class Problem(C.Structure):
+    _fields_ = [("map", MapView), ("points_xy", C.c_void_p), ("n_points", C.c_int32), ("seed", C.c_uint32),
+                ("guess", C.c_double * 3), ("deviation", C.c_double * 3), ("rand_stream", C.c_void_p), ("rand_count", C.c_int64)]
+
+
+class NdtpsoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ndtpso error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise FileNotFoundError(path)
+        _build.build()
+    L = C.CDLL(path)
+    L.ndtpso_abi_version.restype = C.c_int
+    L.ndtpso_device_count.restype = C.c_int
+    L.ndtpso_pso_config_default.argtypes = [C.POINTER(PsoConfig)]
+    L.ndtpso_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.ndtpso_ctx_destroy.argtypes = [C.c_void_p]
+    L.ndtpso_ctx_destroy.restype = None
+    L.ndtpso_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndtpso_last_error.argtypes = [C.c_void_p]
+    L.ndtpso_last_error.restype = C.c_char_p
+    L.ndtpso_ctx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+    L.ndtpso_rand_draws.argtypes = [C.POINTER(PsoConfig)]
+    L.ndtpso_rand_draws.restype = C.c_int64
+    L.ndtpso_align_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.c_void_p, C.c_void_p]
+    L.ndtpso_cost_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.c_int32, C.c_void_p, C.c_void_p]
+    L.ndtpso_batch_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
+    L.ndtpso_batch_solve.argtypes = [C.c_void_p]
+    L.ndtpso_batch_device_results.argtypes = [C.c_void_p]
+    L.ndtpso_batch_device_results.restype = C.c_void_p
+    L.ndtpso_batch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ndtpso_batch_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndtpso_batch_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndtpso_batch_destroy.argtypes = [C.c_void_p]
+    L.ndtpso_batch_destroy.restype = None
+    L.ndtpso_ctx_launch_count.argtypes = [C.c_void_p]
+    L.ndtpso_ctx_launch_count.restype = C.c_int64
+    L.ndtpso_ctx_synchronize.argtypes = [C.c_void_p]
+    L.ndtpso_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(None)
+
+
+class ProblemSet:
+    """Packs flat problem dicts into a `struct ndtpso_problem[]`, keeping the numpy arrays alive.
+
+    A flat problem dict has: points[N,2], mean[R,2], inv_cov[R,4], built[C] (dense) or
+    cell_index[R] (sparse), w_cells, h_cells, width_m, height_m, cell_side, x_min, x_max,
+    y_min, y_max, guess[3], deviation[3], seed, and optionally rand_stream (int32[]).
+    Problems that are the *same dict object's map arrays* share one table on the device.
+    """
+
+    def __init__(self, flats):
+        self.n = len(flats)
+        self.array = (Problem * max(self.n, 1))()
+        self.keep = []
+        for i, f in enumerate(flats):
+            p = self.array[i]
+            pts = self._c(f["points"], np.float64)
+            mean = self._c(f["mean"], np.float64)
+            icov = self._c(f["inv_cov"], np.float64)
+            m = p.map
+            m.w_cells, m.h_cells = int(f["w_cells"]), int(f["h_cells"])
+            m.width_m, m.height_m, m.cell_side = float(f["width_m"]), float(f["height_m"]), float(f["cell_side"])
+            m.x_min, m.x_max, m.y_min, m.y_max = float(f["x_min"]), float(f["x_max"]), float(f["y_min"]), float(f["y_max"])
+            m.mean, m.inv_cov = _ptr(mean), _ptr(icov)
+            if f.get("cell_index") is not None:
+                ci = self._c(f["cell_index"], np.int32)
+                m.n_sparse, m.cell_index, m.built = int(ci.shape[0]), _ptr(ci), C.c_void_p(None)
+            else:
+                built = self._c(f["built"], np.uint8)
+                m.n_sparse, m.cell_index, m.built = -1, C.c_void_p(None), _ptr(built)
+            m.reserved = 0
+            p.points_xy, p.n_points = _ptr(pts), int(pts.shape[0])
+            p.seed = int(f.get("seed", 1)) & 0xFFFFFFFF
+            for k in range(3):
+                p.guess[k] = float(f["guess"][k])
+                p.deviation[k] = float(f["deviation"][k])
+            rs = f.get("rand_stream")
+            if rs is not None:
+                rs = self._c(rs, np.int32)
+                p.rand_stream, p.rand_count = _ptr(rs), int(rs.shape[0])
+            else:
+                p.rand_stream, p.rand_count = C.c_void_p(None), 0
+
+    def _c(self, a, dtype):
+        # identical input arrays map to identical pointers so the library can share tables
+        if isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"]:
+            arr = a
+        else:
+            arr = np.ascontiguousarray(a, dtype=dtype)
+        self.keep.append(arr)
+        return arr
+
+
+class Batch:
+    """A batch resident in HBM (ndtpso_batch_*)."""
+
+    def __init__(self, ctx: "Context", problems: ProblemSet, conf: PsoConfig):
+        self.ctx, self.problems, self.n = ctx, problems, problems.n
+        h = C.c_void_p()
+        ctx._check(ctx.lib.ndtpso_batch_create(ctx.h, problems.n, problems.array, C.byref(conf), C.byref(h)))
+        self.h = h
+
+    def solve(self):
+        self.ctx._check(self.ctx.lib.ndtpso_batch_solve(self.h))
+
+    def device_results_ptr(self) -> int:
+        return int(self.ctx.lib.ndtpso_batch_device_results(self.h) or 0)
+
+    def results(self):
+        pose = np.empty((self.n, 3), dtype=np.float64)
+        cost = np.empty(self.n, dtype=np.float64)
+        self.ctx._check(self.ctx.lib.ndtpso_batch_results(self.h, _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def stats(self):
+        out = np.zeros((self.n, 2), dtype=np.int32)
+        self.ctx._check(self.ctx.lib.ndtpso_batch_stats(self.h, _ptr(out)))
+        return out
+
+    def kernel_times_ms(self):
+        """(K0 compaction, K1 rand stream, K2 PSO) device milliseconds of the last solve."""
+        out = np.zeros(3, dtype=np.float64)
+        self.ctx._check(self.ctx.lib.ndtpso_batch_kernel_times(self.h, _ptr(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ndtpso_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU (ndtpso_ctx_*)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.ndtpso_ctx_create(device, C.byref(h))
+        if rc != OK:
+            raise NdtpsoError(rc, "ndtpso_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+
+    def _check(self, rc):
+        if rc != OK:
+            raise NdtpsoError(rc, (self.lib.ndtpso_last_error(self.h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.ndtpso_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.ndtpso_ctx_set_option(self.h, option, value))
+
+    def align_batch(self, flats, conf: PsoConfig):
+        """pso_optimization for every flat problem: returns (pose[n,3], cost[n])."""
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        pose = np.empty((ps.n, 3), dtype=np.float64)
+        cost = np.empty(ps.n, dtype=np.float64)
+        self._check(self.lib.ndtpso_align_batch(self.h, ps.n, ps.array, C.byref(conf), _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def cost_batch(self, flats, poses):
+        """cost_function of poses[n, m, 3] -> cost[n, m]."""
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(ps.n, -1, 3)
+        out = np.empty(poses.shape[:2], dtype=np.float64)
+        self._check(self.lib.ndtpso_cost_batch(self.h, ps.n, ps.array, poses.shape[1], _ptr(poses), _ptr(out)))
+        return out
+
+    def batch(self, flats, conf: PsoConfig) -> Batch:
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        return Batch(self, ps, conf)
+
+    def launch_count(self) -> int:
+        return int(self.lib.ndtpso_ctx_launch_count(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.ndtpso_ctx_synchronize(self.h))
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0.0)
+        self._check(self.lib.ndtpso_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            self.lib.ndtpso_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

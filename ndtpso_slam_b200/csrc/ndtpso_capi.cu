@@ -1,0 +1,691 @@
+// Host side of libndtpso_b200.so: the C ABI of include/ndtpso_b200.h.
+//
+// A batch is laid out in ONE device allocation ("arena"):
+//   [DevProblem n][DevMap M][points][per map: mean, inv_cov, built | cell_index][host rand streams]   <- uploaded, one H2D
+//   [results n x 4][stats n x 2][per map: hdr, grid, records][device rand streams]                    <- device-only
+// and mirrored (upload part only) in one pinned staging buffer.  Buffers are recycled through a
+// small pool in the context, so a steady stream of align calls performs no cudaMalloc.
+#include "../../include/ndtpso_b200.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ndtpso_kernels.cuh"
+
+using namespace ndtpso;
+
+namespace {
+
+struct PoolBuf {
+  void* ptr;
+  size_t bytes;
+};
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct ndtpso_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  int opt_warps = 0;
+  int64_t opt_smem = 0;
+  int opt_cluster = 0;
+  int64_t launches = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  std::vector<PoolBuf> dev_pool, pin_pool;
+  int smem_attr_set[33] = {0};
+};
+
+struct ndtpso_batch {
+  ndtpso_ctx* ctx = nullptr;
+  int n = 0, n_maps = 0;
+  PsoParams prm{};
+  bool has_pso = false;
+  bool any_device_rng = false;
+  PoolBuf dev{nullptr, 0}, pin{nullptr, 0};
+  size_t upload_bytes = 0;
+  DevProblem* d_probs = nullptr;
+  DevMap* d_maps = nullptr;
+  double* d_out = nullptr;
+  int* d_stats = nullptr;
+  int need_dyn_smem = 0;  // points + records + grid of the largest problem
+  bool solved = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around K0, K1, K2 of the last solve
+};
+
+namespace {
+
+int fail(ndtpso_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                                         \
+  do {                                                                                                              \
+    cudaError_t e__ = (call);                                                                                       \
+    if (e__ != cudaSuccess) {                                                                                       \
+      return fail((ctx), e__ == cudaErrorMemoryAllocation ? NDTPSO_ERR_NOMEM : NDTPSO_ERR_CUDA,                     \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                                             \
+    }                                                                                                               \
+  } while (0)
+
+int pool_take(ndtpso_ctx* ctx, std::vector<PoolBuf>& pool, size_t bytes, bool pinned, PoolBuf* out) {
+  int best = -1;
+  for (int i = 0; i < (int)pool.size(); ++i)
+    if (pool[i].bytes >= bytes && (best < 0 || pool[i].bytes < pool[best].bytes)) best = i;
+  if (best >= 0) {
+    *out = pool[best];
+    pool.erase(pool.begin() + best);
+    return NDTPSO_OK;
+  }
+  void* p = nullptr;
+  const size_t cap = align_up(bytes + bytes / 4, 1 << 16);  // headroom so slightly larger batches still fit
+  if (pinned) {
+    CUDA_TRY(ctx, cudaMallocHost(&p, cap));
+  } else {
+    CUDA_TRY(ctx, cudaMalloc(&p, cap));
+  }
+  *out = PoolBuf{p, cap};
+  return NDTPSO_OK;
+}
+
+void pool_give(std::vector<PoolBuf>& pool, PoolBuf b, bool pinned) {
+  if (!b.ptr) return;
+  if (pool.size() >= 4) {  // keep the pool small: drop the smallest
+    int small = 0;
+    for (int i = 1; i < (int)pool.size(); ++i)
+      if (pool[i].bytes < pool[small].bytes) small = i;
+    if (pool[small].bytes < b.bytes) std::swap(pool[small], b);
+    if (pinned)
+      cudaFreeHost(b.ptr);
+    else
+      cudaFree(b.ptr);
+    return;
+  }
+  pool.push_back(b);
+}
+
+bool is_pow2_double(double v) {
+  if (!(v > 0.) || !std::isfinite(v)) return false;
+  int e;
+  return std::frexp(v, &e) == 0.5;
+}
+
+struct MapKey {
+  const void *mean, *icov, *built, *cidx;
+  int32_t w, h, ns;
+  bool operator<(const MapKey& o) const {
+    return std::tie(mean, icov, built, cidx, w, h, ns) < std::tie(o.mean, o.icov, o.built, o.cidx, o.w, o.h, o.ns);
+  }
+};
+
+int validate_problem(ndtpso_ctx* ctx, const ndtpso_problem& p, int b) {
+  const ndtpso_map_view& m = p.map;
+  char buf[160];
+  if (p.n_points < 0 || (p.n_points > 0 && !p.points_xy)) {
+    snprintf(buf, sizeof buf, "problem %d: bad points (n_points=%d)", b, p.n_points);
+    return fail(ctx, NDTPSO_ERR_ARG, buf);
+  }
+  if (m.w_cells <= 0 || m.h_cells <= 0 || (int64_t)m.w_cells * m.h_cells > (int64_t)INT_MAX / 8 || !(m.cell_side > 0.)) {
+    snprintf(buf, sizeof buf, "problem %d: bad grid %d x %d, cell_side %g", b, m.w_cells, m.h_cells, m.cell_side);
+    return fail(ctx, NDTPSO_ERR_ARG, buf);
+  }
+  if (m.n_sparse < 0) {
+    if (!m.mean || !m.inv_cov || !m.built) {
+      snprintf(buf, sizeof buf, "problem %d: dense map with null table pointer", b);
+      return fail(ctx, NDTPSO_ERR_ARG, buf);
+    }
+  } else {
+    if (m.n_sparse > 0 && (!m.mean || !m.inv_cov || !m.cell_index)) {
+      snprintf(buf, sizeof buf, "problem %d: sparse map with null table pointer", b);
+      return fail(ctx, NDTPSO_ERR_ARG, buf);
+    }
+    if (m.n_sparse > 65534) {
+      snprintf(buf, sizeof buf, "problem %d: sparse map with %d rows (max 65534)", b, m.n_sparse);
+      return fail(ctx, NDTPSO_ERR_LIMIT, buf);
+    }
+  }
+  return NDTPSO_OK;
+}
+
+// Builds the arena for `n` problems; conf == nullptr => cost-only batch (no rand streams).
+int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, size_t extra_upload_bytes,
+                size_t extra_device_bytes, ndtpso_batch** out, size_t* extra_upload_off, size_t* extra_device_off) {
+  if (!ctx || !out || n < 0 || (n > 0 && !problems)) return fail(ctx, NDTPSO_ERR_ARG, "batch: null argument or negative count");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  PsoParams prm{};
+  if (conf) {
+    if (conf->iterations < 0 || conf->population < 0) return fail(ctx, NDTPSO_ERR_ARG, "PSO config: negative iterations/population");
+    const int64_t draws = ndtpso_rand_draws(conf);
+    if (draws > INT_MAX / 2) return fail(ctx, NDTPSO_ERR_LIMIT, "PSO config: 3+3P+6PI exceeds the supported stream length");
+    prm.P = conf->population;
+    prm.I = conf->iterations;
+    prm.w = conf->w;
+    prm.c1 = conf->c1;
+    prm.c2 = conf->c2;
+    prm.wd = conf->w_dumping;
+    prm.n_draws = (int)draws;
+    if (pso_fixed_smem_bytes(prm.P) > ctx->max_smem_optin - 1024)
+      return fail(ctx, NDTPSO_ERR_LIMIT, "PSO config: population too large for one CTA's shared memory");
+  }
+  for (int b = 0; b < n; ++b) {
+    int rc = validate_problem(ctx, problems[b], b);
+    if (rc) return rc;
+    if (conf && problems[b].rand_stream && problems[b].rand_count < prm.n_draws)
+      return fail(ctx, NDTPSO_ERR_ARG, "problem: rand_stream shorter than 3+3P+6PI");
+  }
+
+  // ---- maps: dedupe by identity of the table pointers
+  std::map<MapKey, int> map_ids;
+  std::vector<const ndtpso_map_view*> maps;
+  std::vector<int> map_of(n);
+  for (int b = 0; b < n; ++b) {
+    const ndtpso_map_view& m = problems[b].map;
+    MapKey k{m.mean, m.inv_cov, m.built, m.cell_index, m.w_cells, m.h_cells, m.n_sparse};
+    auto it = map_ids.find(k);
+    if (it == map_ids.end()) {
+      it = map_ids.emplace(k, (int)maps.size()).first;
+      maps.push_back(&m);
+    }
+    map_of[b] = it->second;
+  }
+  const int M = (int)maps.size();
+
+  // ---- arena layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes);
+    return o;
+  };
+  const size_t o_probs = take(sizeof(DevProblem) * (size_t)std::max(n, 1));
+  const size_t o_maps = take(sizeof(DevMap) * (size_t)std::max(M, 1));
+  std::vector<size_t> o_pts(n), o_rnd(n, 0);
+  for (int b = 0; b < n; ++b) o_pts[b] = take((size_t)problems[b].n_points * 16);
+  std::vector<size_t> o_mean(M), o_icov(M), o_built(M), o_cidx(M);
+  std::vector<int> rows(M);
+  for (int i = 0; i < M; ++i) {
+    const ndtpso_map_view& m = *maps[i];
+    const int ncells = m.w_cells * m.h_cells;
+    rows[i] = m.n_sparse >= 0 ? m.n_sparse : ncells;
+    o_mean[i] = take((size_t)rows[i] * 16);
+    o_icov[i] = take((size_t)rows[i] * 32);
+    o_built[i] = m.n_sparse >= 0 ? 0 : take((size_t)ncells);
+    o_cidx[i] = m.n_sparse >= 0 ? take((size_t)rows[i] * 4) : 0;
+  }
+  bool any_device_rng = false;
+  if (conf)
+    for (int b = 0; b < n; ++b) {
+      if (problems[b].rand_stream)
+        o_rnd[b] = take((size_t)prm.n_draws * 4);
+      else
+        any_device_rng = true;
+    }
+  const size_t o_extra_up = take(extra_upload_bytes);
+  const size_t upload_bytes = off;
+  const size_t o_out = take(sizeof(double) * 4 * (size_t)std::max(n, 1));
+  const size_t o_stats = take(sizeof(int) * 2 * (size_t)std::max(n, 1));
+  std::vector<size_t> o_hdr(M), o_grid(M), o_rec(M);
+  for (int i = 0; i < M; ++i) {
+    const ndtpso_map_view& m = *maps[i];
+    o_hdr[i] = take(sizeof(int) * HDR_WORDS);
+    o_grid[i] = take((size_t)m.w_cells * m.h_cells * 2 + 16);
+    o_rec[i] = take((size_t)rows[i] * 48 + 16);
+  }
+  if (conf)
+    for (int b = 0; b < n; ++b)
+      if (!problems[b].rand_stream) o_rnd[b] = take((size_t)prm.n_draws * 4);
+  const size_t o_extra_dev = take(extra_device_bytes);
+  const size_t total_bytes = off;
+
+  ndtpso_batch* bt = new (std::nothrow) ndtpso_batch();
+  if (!bt) return fail(ctx, NDTPSO_ERR_NOMEM, "batch: host allocation failed");
+  bt->ctx = ctx;
+  bt->n = n;
+  bt->n_maps = M;
+  bt->prm = prm;
+  bt->has_pso = conf != nullptr;
+  bt->any_device_rng = any_device_rng;
+  bt->upload_bytes = upload_bytes;
+  int rc = pool_take(ctx, ctx->dev_pool, total_bytes, false, &bt->dev);
+  if (rc == NDTPSO_OK) rc = pool_take(ctx, ctx->pin_pool, upload_bytes, true, &bt->pin);
+  if (rc != NDTPSO_OK) {
+    ndtpso_batch_destroy(bt);
+    return rc;
+  }
+  unsigned char* h = static_cast<unsigned char*>(bt->pin.ptr);
+  unsigned char* d = static_cast<unsigned char*>(bt->dev.ptr);
+  bt->d_probs = reinterpret_cast<DevProblem*>(d + o_probs);
+  bt->d_maps = reinterpret_cast<DevMap*>(d + o_maps);
+  bt->d_out = reinterpret_cast<double*>(d + o_out);
+  bt->d_stats = reinterpret_cast<int*>(d + o_stats);
+
+  // ---- fill the staging buffer
+  DevMap* hm = reinterpret_cast<DevMap*>(h + o_maps);
+  std::vector<int> map_dyn(M, 0);
+  for (int i = 0; i < M; ++i) {
+    const ndtpso_map_view& m = *maps[i];
+    const int ncells = m.w_cells * m.h_cells;
+    DevMap dm{};
+    dm.x_min = m.x_min;
+    dm.x_max = m.x_max;
+    dm.y_min = m.y_min;
+    dm.y_max = m.y_max;
+    dm.hw = m.width_m / 2.;
+    dm.hh = m.height_m / 2.;
+    dm.cs = m.cell_side;
+    dm.cs_pow2 = is_pow2_double(m.cell_side) ? 1 : 0;
+    dm.inv_cs = 1.0 / m.cell_side;
+    dm.gw = m.w_cells;
+    dm.gh = m.h_cells;
+    dm.ncells = ncells;
+    dm.n_sparse = m.n_sparse;
+    dm.mean = reinterpret_cast<const double*>(d + o_mean[i]);
+    dm.icov = reinterpret_cast<const double*>(d + o_icov[i]);
+    dm.built = m.n_sparse >= 0 ? nullptr : d + o_built[i];
+    dm.cell_index = m.n_sparse >= 0 ? reinterpret_cast<const int*>(d + o_cidx[i]) : nullptr;
+    dm.grid = reinterpret_cast<unsigned short*>(d + o_grid[i]);
+    dm.rec = reinterpret_cast<double*>(d + o_rec[i]);
+    dm.hdr = reinterpret_cast<int*>(d + o_hdr[i]);
+    hm[i] = dm;
+    if (rows[i]) {
+      memcpy(h + o_mean[i], m.mean, (size_t)rows[i] * 16);
+      memcpy(h + o_icov[i], m.inv_cov, (size_t)rows[i] * 32);
+    }
+    // shared-memory need of this table (built cells and their bounding box), known on the host for free
+    int n_rec = 0, ax = INT_MAX, ay = INT_MAX, bx = -1, by = -1;
+    auto note = [&](int cell) {
+      const int ix = cell % m.w_cells, iy = cell / m.w_cells;
+      ax = std::min(ax, ix);
+      ay = std::min(ay, iy);
+      bx = std::max(bx, ix);
+      by = std::max(by, iy);
+      ++n_rec;
+    };
+    if (m.n_sparse >= 0) {
+      if (rows[i]) memcpy(h + o_cidx[i], m.cell_index, (size_t)rows[i] * 4);
+      for (int r = 0; r < rows[i]; ++r) {
+        const int cell = m.cell_index[r];
+        if (cell < 0 || cell >= ncells || (r > 0 && cell <= m.cell_index[r - 1])) {
+          ndtpso_batch_destroy(bt);
+          return fail(ctx, NDTPSO_ERR_ARG, "sparse map: cell_index must be strictly ascending and inside the grid");
+        }
+        note(cell);
+      }
+    } else {
+      memcpy(h + o_built[i], m.built, (size_t)ncells);
+      for (int c = 0; c < ncells; ++c)
+        if (m.built[c]) note(c);
+    }
+    map_dyn[i] = n_rec ? n_rec * 48 + (((bx - ax + 1) * (by - ay + 1) * 2 + 15) & ~15) : 0;
+  }
+  DevProblem* hp = reinterpret_cast<DevProblem*>(h + o_probs);
+  int need = 0;
+  for (int b = 0; b < n; ++b) {
+    const ndtpso_problem& p = problems[b];
+    DevProblem dp{};
+    dp.pts = reinterpret_cast<const double2*>(d + o_pts[b]);
+    dp.n_pts = p.n_points;
+    dp.map_id = map_of[b];
+    for (int k = 0; k < 3; ++k) {
+      dp.guess[k] = p.guess[k];
+      dp.dev[k] = p.deviation[k];
+    }
+    dp.seed = p.seed;
+    dp.rnd = conf ? reinterpret_cast<const int*>(d + o_rnd[b]) : nullptr;
+    dp.rnd_from_host = (conf && p.rand_stream) ? 1 : 0;
+    hp[b] = dp;
+    if (p.n_points) memcpy(h + o_pts[b], p.points_xy, (size_t)p.n_points * 16);
+    if (conf && p.rand_stream) memcpy(h + o_rnd[b], p.rand_stream, (size_t)prm.n_draws * 4);
+    need = std::max(need, p.n_points * 16 + map_dyn[map_of[b]]);
+  }
+  bt->need_dyn_smem = need;
+  if (extra_upload_off) *extra_upload_off = o_extra_up;
+  if (extra_device_off) *extra_device_off = o_extra_dev;
+  *out = bt;
+  return NDTPSO_OK;
+}
+
+int batch_upload(ndtpso_batch* bt) {
+  ndtpso_ctx* ctx = bt->ctx;
+  CUDA_TRY(ctx, cudaMemcpyAsync(bt->dev.ptr, bt->pin.ptr, bt->upload_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NDTPSO_OK;
+}
+
+int pick_warps(const ndtpso_ctx* ctx) {
+  int w = ctx->opt_warps;
+  if (w == 4 || w == 8 || w == 16 || w == 32) return w;
+  return 8;
+}
+
+int pick_smem(const ndtpso_ctx* ctx, int fixed_bytes, int need_dyn) {
+  int64_t s = ctx->opt_smem > 0 ? ctx->opt_smem : (int64_t)fixed_bytes + need_dyn;
+  s = std::max<int64_t>(s, fixed_bytes);
+  s = std::min<int64_t>(s, ctx->max_smem_optin);
+  return (int)((s + 15) & ~15);
+}
+
+template <int NW>
+int launch_pso(ndtpso_batch* bt, int smem) {
+  ndtpso_ctx* ctx = bt->ctx;
+  if (ctx->smem_attr_set[NW] < smem) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(pso_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    ctx->smem_attr_set[NW] = ctx->max_smem_optin;
+  }
+  PsoParams prm = bt->prm;
+  prm.smem_bytes = smem;
+  pso_kernel<NW><<<bt->n, NW * 32, smem, ctx->stream>>>(bt->d_probs, bt->d_maps, prm, bt->d_out, bt->d_stats);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return NDTPSO_OK;
+}
+
+int launch_compact(ndtpso_batch* bt) {
+  ndtpso_ctx* ctx = bt->ctx;
+  if (bt->n_maps == 0) return NDTPSO_OK;
+  compact_map_kernel<<<bt->n_maps, K0_THREADS, 0, ctx->stream>>>(bt->d_maps);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return NDTPSO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ndtpso_abi_version(void) { return NDTPSO_ABI_VERSION; }
+
+void ndtpso_pso_config_default(ndtpso_pso_config* conf) {
+  if (!conf) return;
+  conf->iterations = 50;   // PSO_ITERATIONS        config.h:20
+  conf->population = 30;   // PSO_POPULATION_SIZE   config.h:21
+  conf->num_threads = -1;  //                       config.h:30
+  conf->reserved = 0;
+  conf->w = .8;            // PSO_W                 config.h:23
+  conf->c1 = 2.;           // PSO_C1                config.h:24
+  conf->c2 = 2.;           // PSO_C2                config.h:25
+  conf->w_dumping = 1.;    // PSO_W_DUMPING_COEF    config.h:22
+}
+
+int64_t ndtpso_rand_draws(const ndtpso_pso_config* conf) {
+  if (!conf) return 0;
+  const int64_t P = conf->population, I = conf->iterations;
+  return 3 + 3 * P + 6 * P * I;
+}
+
+int ndtpso_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ndtpso_ctx_create(int device, ndtpso_ctx** out) {
+  if (!out) return NDTPSO_ERR_ARG;
+  *out = nullptr;
+  const int n = ndtpso_device_count();
+  if (n <= 0 || device < 0 || device >= n) return NDTPSO_ERR_NODEVICE;
+  ndtpso_ctx* ctx = new (std::nothrow) ndtpso_ctx();
+  if (!ctx) return NDTPSO_ERR_NOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return NDTPSO_ERR_CUDA;
+  }
+  if (prop.major < 10) {  // sm_100a code only
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return NDTPSO_ERR_NODEVICE;
+  }
+  ctx->stream = ctx->own_stream;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = ctx;
+  return NDTPSO_OK;
+}
+
+void ndtpso_ctx_destroy(ndtpso_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& b : ctx->dev_pool) cudaFree(b.ptr);
+  for (auto& b : ctx->pin_pool) cudaFreeHost(b.ptr);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int ndtpso_ctx_set_stream(ndtpso_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return NDTPSO_ERR_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return NDTPSO_OK;
+}
+
+const char* ndtpso_last_error(const ndtpso_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return NDTPSO_ERR_ARG;
+  switch (option) {
+    case NDTPSO_OPT_WARPS_PER_CTA:
+      if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) return fail(ctx, NDTPSO_ERR_ARG, "warps per CTA must be 0, 4, 8, 16 or 32");
+      ctx->opt_warps = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_SMEM_BYTES:
+      if (value < 0 || value > ctx->max_smem_optin) return fail(ctx, NDTPSO_ERR_ARG, "shared memory bytes out of range");
+      ctx->opt_smem = value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_CLUSTER:
+      if (value < 0 || value > 1) return fail(ctx, NDTPSO_ERR_ARG, "cluster size not supported");
+      ctx->opt_cluster = (int)value;
+      return NDTPSO_OK;
+    default:
+      return fail(ctx, NDTPSO_ERR_ARG, "unknown option");
+  }
+}
+
+int64_t ndtpso_ctx_launch_count(const ndtpso_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ndtpso_ctx_synchronize(ndtpso_ctx* ctx) {
+  if (!ctx) return NDTPSO_ERR_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NDTPSO_OK;
+}
+
+int ndtpso_batch_create(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out) {
+  if (!conf) return fail(ctx, NDTPSO_ERR_ARG, "batch_create: null config");
+  if (out) *out = nullptr;
+  ndtpso_batch* bt = nullptr;
+  int rc = batch_build(ctx, n, problems, conf, 0, 0, &bt, nullptr, nullptr);
+  if (rc) return rc;
+  rc = batch_upload(bt);
+  if (rc) {
+    ndtpso_batch_destroy(bt);
+    return rc;
+  }
+  *out = bt;
+  return NDTPSO_OK;
+}
+
+int ndtpso_batch_solve(ndtpso_batch* bt) {
+  if (!bt || !bt->has_pso) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = bt->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (bt->n == 0) return NDTPSO_OK;
+  if (!bt->ev[0])
+    for (auto& e : bt->ev) CUDA_TRY(ctx, cudaEventCreate(&e));
+  CUDA_TRY(ctx, cudaEventRecord(bt->ev[0], ctx->stream));
+  int rc = launch_compact(bt);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(bt->ev[1], ctx->stream));
+  if (bt->any_device_rng) {
+    rng_fill_kernel<<<(bt->n + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, ctx->stream>>>(bt->d_probs, bt->n, bt->prm.n_draws);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  CUDA_TRY(ctx, cudaEventRecord(bt->ev[2], ctx->stream));
+  const int fixed = pso_fixed_smem_bytes(bt->prm.P);
+  const int smem = pick_smem(ctx, fixed, bt->need_dyn_smem);
+  switch (pick_warps(ctx)) {
+    case 4: rc = launch_pso<4>(bt, smem); break;
+    case 16: rc = launch_pso<16>(bt, smem); break;
+    case 32: rc = launch_pso<32>(bt, smem); break;
+    default: rc = launch_pso<8>(bt, smem); break;
+  }
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(bt->ev[3], ctx->stream));
+  bt->solved = true;
+  return NDTPSO_OK;
+}
+
+int ndtpso_batch_kernel_times(ndtpso_batch* bt, double* out_ms) {
+  if (!bt || !out_ms) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = bt->ctx;
+  if (!bt->solved || !bt->ev[0]) return fail(ctx, NDTPSO_ERR_ARG, "batch_kernel_times before batch_solve");
+  CUDA_TRY(ctx, cudaEventSynchronize(bt->ev[3]));
+  for (int i = 0; i < 3; ++i) {
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, bt->ev[i], bt->ev[i + 1]));
+    out_ms[i] = ms;
+  }
+  return NDTPSO_OK;
+}
+
+void* ndtpso_batch_device_results(ndtpso_batch* bt) { return bt ? bt->d_out : nullptr; }
+
+int ndtpso_batch_results(ndtpso_batch* bt, double* out_pose, double* out_cost) {
+  if (!bt) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = bt->ctx;
+  if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_results before batch_solve");
+  if (bt->n == 0) return NDTPSO_OK;
+  // results come back through the (already consumed) head of the pinned staging buffer
+  double* h = static_cast<double*>(bt->pin.ptr);
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, bt->d_out, sizeof(double) * 4 * (size_t)bt->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < bt->n; ++b) {
+    if (out_pose) {
+      out_pose[3 * b] = h[4 * b];
+      out_pose[3 * b + 1] = h[4 * b + 1];
+      out_pose[3 * b + 2] = h[4 * b + 2];
+    }
+    if (out_cost) out_cost[b] = h[4 * b + 3];
+  }
+  return NDTPSO_OK;
+}
+
+int ndtpso_batch_stats(ndtpso_batch* bt, int32_t* out) {
+  if (!bt || !out) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = bt->ctx;
+  if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_stats before batch_solve");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(out, bt->d_stats, sizeof(int) * 2 * (size_t)bt->n, cudaMemcpyDeviceToHost));
+  return NDTPSO_OK;
+}
+
+void ndtpso_batch_destroy(ndtpso_batch* bt) {
+  if (!bt) return;
+  ndtpso_ctx* ctx = bt->ctx;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);  // nothing in flight may still read the buffers
+    pool_give(ctx->dev_pool, bt->dev, false);
+    pool_give(ctx->pin_pool, bt->pin, true);
+    for (auto& e : bt->ev)
+      if (e) cudaEventDestroy(e);
+  }
+  delete bt;
+}
+
+int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, double* out_pose,
+                       double* out_cost) {
+  if (!ctx || !conf || (n > 0 && !out_pose)) return fail(ctx, NDTPSO_ERR_ARG, "align_batch: null argument");
+  ndtpso_batch* bt = nullptr;
+  int rc = ndtpso_batch_create(ctx, n, problems, conf, &bt);
+  if (rc) return rc;
+  rc = ndtpso_batch_solve(bt);
+  if (rc == NDTPSO_OK) rc = ndtpso_batch_results(bt, out_pose, out_cost);
+  ndtpso_batch_destroy(bt);
+  return rc;
+}
+
+int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int32_t n_poses, const double* poses, double* out_cost) {
+  if (!ctx || n_poses < 0 || (n > 0 && n_poses > 0 && (!poses || !out_cost))) return fail(ctx, NDTPSO_ERR_ARG, "cost_batch: null argument");
+  if (n == 0 || n_poses == 0) return NDTPSO_OK;
+  const size_t pose_bytes = sizeof(double) * 3 * (size_t)n * n_poses;
+  const size_t cost_bytes = sizeof(double) * (size_t)n * n_poses;
+  ndtpso_batch* bt = nullptr;
+  size_t o_up = 0, o_dev = 0;
+  int rc = batch_build(ctx, n, problems, nullptr, pose_bytes, cost_bytes, &bt, &o_up, &o_dev);
+  if (rc) return rc;
+  auto cleanup = [&](int code) {
+    ndtpso_batch_destroy(bt);
+    return code;
+  };
+  memcpy(static_cast<unsigned char*>(bt->pin.ptr) + o_up, poses, pose_bytes);
+  rc = batch_upload(bt);
+  if (rc) return cleanup(rc);
+  rc = launch_compact(bt);
+  if (rc) return cleanup(rc);
+  constexpr int NW = 8;
+  const int smem = pick_smem(ctx, 16, bt->need_dyn_smem);
+  cudaError_t e = cudaFuncSetAttribute(cost_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
+  unsigned char* d = static_cast<unsigned char*>(bt->dev.ptr);
+  cost_kernel<NW><<<n, NW * 32, smem, ctx->stream>>>(bt->d_probs, bt->d_maps, n_poses, reinterpret_cast<const double*>(d + o_up),
+                                                     reinterpret_cast<double*>(d + o_dev), smem);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
+  ctx->launches++;
+  e = cudaMemcpyAsync(out_cost, d + o_dev, cost_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
+  return cleanup(NDTPSO_OK);
+}
+
+int ndtpso_measure_fp64_peak(ndtpso_ctx* ctx, double* out_tflops) {
+  if (!ctx || !out_tflops) return NDTPSO_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+  double* d = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&d, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best_ms = std::min(best_ms, (double)ms);
+    ctx->launches++;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e));
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+  *out_tflops = flops / (best_ms * 1e-3) / 1e12;
+  return NDTPSO_OK;
+}
+
+}  // extern "C"

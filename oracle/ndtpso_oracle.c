@@ -33,14 +33,15 @@ typedef struct {
 
 void orc_srand(orc_rng* g, uint32_t seed) {
   if (seed == 0) seed = 1;
-  long long word = seed;
-  g->r[0] = (int32_t)seed;
+  int32_t word = (int32_t)seed; /* glibc keeps `word` in an int32_t: seeds >= 2^31 go negative */
+  g->r[0] = word;
   for (int i = 1; i < 31; ++i) {
-    long long hi = word / 127773;
-    long long lo = word % 127773;
-    word = 16807 * lo - 2836 * hi;
-    if (word < 0) word += 2147483647;
-    g->r[i] = (int32_t)word;
+    const long long hi = word / 127773;
+    const long long lo = word % 127773;
+    long long t = 16807 * lo - 2836 * hi;
+    if (t < 0) t += 2147483647;
+    word = (int32_t)t;
+    g->r[i] = word;
   }
   g->f = 3;
   g->b = 0;

@@ -1,0 +1,137 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden outputs and the oracle.
+
+Tolerances (BASELINE.json north_star): |pose - ref| <= 1e-4 per component, |score - ref| <= 1e-5 relative.
+The device sums a scan's scores in a warp-tree order and fuses multiply-adds, so scores are not
+bit-identical; poses usually are (the swarm update itself is computed without contraction).
+"""
+import numpy as np
+import pytest
+
+from ndtpso_slam_b200 import capi
+from tests.problems import POSE_ATOL, SCORE_RTOL, SOLVED, empty_points, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def conf_of(c):
+    return capi.PsoConfig.make(population=c["P"], iterations=c["I"], w=c["w"], c1=c["c1"], c2=c["c2"], w_dumping=c["w_dumping"])
+
+
+@pytest.mark.parametrize("case,inputs", SOLVED)
+@pytest.mark.parametrize("sparse", [False, True])
+def test_pso_vs_golden(golden, ctx, case, inputs, sparse):
+    c, flats = golden.problems(case, inputs, sparse=sparse)
+    if case == "edge_empty_scan":
+        flats = [empty_points(f) for f in flats]
+    pose, cost = ctx.align_batch(flats, conf_of(c))
+    assert np.abs(pose - c["pose"]).max() <= POSE_ATOL, (case, pose, c["pose"])
+    assert rel_err(cost, c["cost"]).max() <= SCORE_RTOL, (case, cost, c["cost"])
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_cost_vs_golden(golden, ctx, name):
+    flat = golden.flat(name)
+    poses = golden.z[f"{name}/cost_poses"]
+    want = golden.z[f"{name}/cost_values"]
+    got = ctx.cost_batch([flat], poses[None])[0]
+    assert rel_err(got, want).max() <= 1e-12
+    assert (got[want == 0] == 0).all()
+
+
+def test_device_rand_equals_host_stream(golden, oracle, ctx):
+    """K1's on-device glibc rand() == the host-drawn stream (drop-in mode), bit for bit in the result."""
+    c, flats = golden.problems("cfg1")
+    n = 3 + 3 * c["P"] + 6 * c["P"] * c["I"]
+    hosted = []
+    for f in flats[:6]:
+        g = dict(f)
+        g["rand_stream"] = oracle.rand_stream(f["seed"], n)
+        g["seed"] = 0
+        hosted.append(g)
+    p1, c1 = ctx.align_batch(flats[:6], conf_of(c))
+    p2, c2 = ctx.align_batch(hosted, conf_of(c))
+    assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 42, 123456789, 4294967295])
+def test_device_rand_seeds(golden, oracle, ctx, seed):
+    """Unusual seeds (0 -> 1, >= 2^31) go through K1 and must match the oracle run on the same seed."""
+    c = golden.case("cfg1")
+    f = golden.flat("cfg1")
+    f.update(guess=c["guess"], deviation=c["deviation"], seed=seed)
+    pose, cost = ctx.align_batch([f], capi.PsoConfig.make(population=12, iterations=6))
+    po, co, _ = oracle.pso(f, c["guess"], c["deviation"], 12, 6, seed=seed)
+    assert np.abs(pose[0] - po).max() <= POSE_ATOL and rel_err(cost[0], co) <= SCORE_RTOL
+
+
+def test_batch_order_and_sharding_invariance(golden, ctx):
+    """Each problem's result is independent of what else is in the batch and of its position."""
+    c, flats = golden.problems("cfg1")
+    cf = conf_of(c)
+    full_pose, full_cost = ctx.align_batch(flats, cf)
+    perm = np.random.default_rng(3).permutation(len(flats))
+    pp, pc = ctx.align_batch([flats[i] for i in perm], cf)
+    assert np.array_equal(pp, full_pose[perm]) and np.array_equal(pc, full_cost[perm])
+    half = len(flats) // 2
+    a = ctx.align_batch(flats[:half], cf)
+    b = ctx.align_batch(flats[half:], cf)
+    assert np.array_equal(np.vstack([a[0], b[0]]), full_pose)
+    one = ctx.align_batch(flats[5:6], cf)
+    assert np.array_equal(one[0][0], full_pose[5])
+
+
+def test_deterministic_and_resolvable(golden, ctx):
+    c, flats = golden.problems("cfg2")
+    bt = ctx.batch(flats, conf_of(c))
+    bt.solve()
+    p1, c1 = bt.results()
+    bt.solve()
+    p2, c2 = bt.results()
+    st = bt.stats()
+    bt.close()
+    assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
+    assert np.abs(p1 - c["pose"]).max() <= POSE_ATOL
+    # rounds = iterations + gbest improvements that did not fall on an iteration's last particle
+    assert (st[:, 0] >= c["I"]).all() and (st[:, 0] <= c["I"] + st[:, 1]).all()
+
+
+def test_oracle_on_fresh_inputs(oracle, ctx):
+    """Seeded random map + scan (not from the reference's map builder): CUDA vs oracle."""
+    rng = np.random.default_rng(11)
+    gw = gh = 40
+    n = gw * gh
+    built = (rng.random(n) < 0.2).astype(np.uint8)
+    cx = (np.arange(n) % gw + 0.5) * 0.5 - 10.0
+    cy = (np.arange(n) // gw + 0.5) * 0.5 - 10.0
+    mean = np.stack([cx, cy], 1) + rng.normal(size=(n, 2)) * 0.05
+    a = rng.uniform(5, 60, n); b = rng.uniform(5, 60, n); r = rng.uniform(-0.5, 0.5, n) * np.sqrt(a * b)
+    icov = np.stack([a, r, r, b], 1)
+    pts = rng.uniform(-9, 9, size=(777, 2))
+    flat = dict(points=pts, mean=mean, inv_cov=icov, built=built, w_cells=gw, h_cells=gh, width_m=20.0, height_m=20.0,
+                cell_side=0.5, x_min=-10.0, x_max=10.0, y_min=-10.0, y_max=10.0)
+    flats = []
+    for s in range(1, 9):
+        f = dict(flat)
+        f.update(guess=(0.1, -0.2, 0.05), deviation=(0.3, 0.3, 0.05), seed=s)
+        flats.append(f)
+    pose, cost = ctx.align_batch(flats, capi.PsoConfig.make(population=25, iterations=12))
+    for i, f in enumerate(flats):
+        po, co, _ = oracle.pso(f, f["guess"], f["deviation"], 25, 12, seed=f["seed"])
+        assert np.abs(pose[i] - po).max() <= POSE_ATOL
+        assert rel_err(cost[i], co) <= SCORE_RTOL
+    poses = np.array(flat["points"][:50].tolist())[:, :1] * 0 + rng.normal(size=(50, 3))
+    got = ctx.cost_batch([flat], poses[None])[0]
+    assert rel_err(got, oracle.cost_many(flat, poses)).max() <= 1e-12
+
+
+def test_argument_errors(golden, ctx):
+    c, flats = golden.problems("cfg1")
+    bad = dict(flats[0]); bad["w_cells"] = 0
+    with pytest.raises(capi.NdtpsoError) as e:
+        ctx.align_batch([bad], conf_of(c))
+    assert e.value.code == capi.ERR_ARG
+    with pytest.raises(capi.NdtpsoError) as e:
+        ctx.align_batch(flats[:1], capi.PsoConfig.make(population=100000, iterations=1))
+    assert e.value.code == capi.ERR_LIMIT
+    pose, cost = ctx.align_batch([], conf_of(c))
+    assert pose.shape == (0, 3)

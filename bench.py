@@ -209,7 +209,8 @@ def run_gpu_arm(args):
 
     flats = make_problems(B, rank)
     ctx = capi.Context(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-legacy) stream shared by torch events, NCCL and the library
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     conf = capi.PsoConfig.make(population=P, iterations=I)
 

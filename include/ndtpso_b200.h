@@ -114,7 +114,10 @@ const char* ndtpso_last_error(const ndtpso_ctx* ctx);
 enum {
   NDTPSO_OPT_WARPS_PER_CTA = 1, /* 0 = auto */
   NDTPSO_OPT_SMEM_BYTES = 2,    /* dynamic shared memory per CTA; 0 = auto */
-  NDTPSO_OPT_CLUSTER = 3        /* CTAs cooperating on one problem; 0 = auto */
+  NDTPSO_OPT_CLUSTER = 3,       /* CTAs cooperating on one problem; 0 = auto */
+  NDTPSO_OPT_KERNEL = 4,        /* 0 = auto, 1 = warp-per-particle (generic), 2 = point-sliced */
+  NDTPSO_OPT_POINTS_PER_THREAD = 5, /* point-sliced kernel: scan points held per thread; 0 = auto */
+  NDTPSO_OPT_CANDIDATE_BATCH = 6   /* point-sliced kernel: candidates scored together (1, 2, 4); 0 = auto */
 };
 int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value);
 

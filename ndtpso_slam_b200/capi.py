@@ -14,7 +14,8 @@ import numpy as np
 from . import build as _build
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_LIMIT = 0, -1, -2, -3, -4, -5
-OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER = 1, 2, 3
+OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREAD, OPT_CANDIDATE_BATCH = 1, 2, 3, 4, 5, 6
+KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 
 #: every symbol include/ndtpso_b200.h declares
 EXPORTS = [
@@ -134,9 +135,10 @@ class ProblemSet:
             m.reserved = 0
             p.points_xy, p.n_points = _ptr(pts), int(pts.shape[0])
             p.seed = int(f.get("seed", 1)) & 0xFFFFFFFF
+            guess, dev = f.get("guess", (0., 0., 0.)), f.get("deviation", (0., 0., 0.))
             for k in range(3):
-                p.guess[k] = float(f["guess"][k])
-                p.deviation[k] = float(f["deviation"][k])
+                p.guess[k] = float(guess[k])
+                p.deviation[k] = float(dev[k])
             rs = f.get("rand_stream")
             if rs is not None:
                 rs = self._c(rs, np.int32)

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ndtpso_kernels.cuh"
+#include "ndtpso_pso_sliced.cuh"
 
 using namespace ndtpso;
 
@@ -42,6 +43,9 @@ struct ndtpso_ctx {
   int opt_warps = 0;
   int64_t opt_smem = 0;
   int opt_cluster = 0;
+  int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
+  int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
+  int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
@@ -62,6 +66,10 @@ struct ndtpso_batch {
   double* d_out = nullptr;
   int* d_stats = nullptr;
   int need_dyn_smem = 0;  // points + records + grid of the largest problem
+  int max_pts = 0;        // largest scan
+  int max_table_smem = 0; // records + grid of the largest table
+  bool all_compact = true;  // every table has <= 65534 built cells
+  bool all_symmetric = true;  // every built cell has S01 == S10 bit for bit (NDTCell::build always does)
   bool solved = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around K0, K1, K2 of the last solve
 };
@@ -242,8 +250,8 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   for (int i = 0; i < M; ++i) {
     const ndtpso_map_view& m = *maps[i];
     o_hdr[i] = take(sizeof(int) * HDR_WORDS);
-    o_grid[i] = take((size_t)m.w_cells * m.h_cells * 2 + 16);
-    o_rec[i] = take((size_t)rows[i] * 48 + 16);
+    o_grid[i] = take(((size_t)m.w_cells * m.h_cells + 1) * 2 + 16);  // row strip (<= all rows) + null slot
+    o_rec[i] = take(((size_t)rows[i] + 1) * 48);                      // records + null record
   }
   if (conf)
     for (int b = 0; b < n; ++b)
@@ -287,8 +295,8 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     dm.hw = m.width_m / 2.;
     dm.hh = m.height_m / 2.;
     dm.cs = m.cell_side;
-    dm.cs_pow2 = is_pow2_double(m.cell_side) ? 1 : 0;
     dm.inv_cs = 1.0 / m.cell_side;
+    dm.fast_geom = (is_pow2_double(m.cell_side) && m.x_min == -m.x_max && m.y_min == -m.y_max) ? 1 : 0;
     dm.gw = m.w_cells;
     dm.gh = m.h_cells;
     dm.ncells = ncells;
@@ -305,13 +313,11 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
       memcpy(h + o_mean[i], m.mean, (size_t)rows[i] * 16);
       memcpy(h + o_icov[i], m.inv_cov, (size_t)rows[i] * 32);
     }
-    // shared-memory need of this table (built cells and their bounding box), known on the host for free
-    int n_rec = 0, ax = INT_MAX, ay = INT_MAX, bx = -1, by = -1;
+    // shared-memory need of this table (built cells and the grid rows they span), known on the host for free
+    int n_rec = 0, ay = INT_MAX, by = -1;
     auto note = [&](int cell) {
-      const int ix = cell % m.w_cells, iy = cell / m.w_cells;
-      ax = std::min(ax, ix);
+      const int iy = cell / m.w_cells;
       ay = std::min(ay, iy);
-      bx = std::max(bx, ix);
       by = std::max(by, iy);
       ++n_rec;
     };
@@ -324,13 +330,20 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
           return fail(ctx, NDTPSO_ERR_ARG, "sparse map: cell_index must be strictly ascending and inside the grid");
         }
         note(cell);
+        if (memcmp(&m.inv_cov[4 * (size_t)r + 1], &m.inv_cov[4 * (size_t)r + 2], sizeof(double)) != 0) bt->all_symmetric = false;
       }
     } else {
       memcpy(h + o_built[i], m.built, (size_t)ncells);
       for (int c = 0; c < ncells; ++c)
-        if (m.built[c]) note(c);
+        if (m.built[c]) {
+          note(c);
+          if (memcmp(&m.inv_cov[4 * (size_t)c + 1], &m.inv_cov[4 * (size_t)c + 2], sizeof(double)) != 0) bt->all_symmetric = false;
+        }
     }
-    map_dyn[i] = n_rec ? n_rec * 48 + (((bx - ax + 1) * (by - ay + 1) * 2 + 15) & ~15) : 0;
+    const int nrows = n_rec ? by - ay + 1 : 0;
+    map_dyn[i] = (n_rec + 1) * 48 + round16((nrows * m.w_cells + 1) * 2);
+    bt->max_table_smem = std::max(bt->max_table_smem, map_dyn[i]);
+    if (n_rec > 65534) bt->all_compact = false;
   }
   DevProblem* hp = reinterpret_cast<DevProblem*>(h + o_probs);
   int need = 0;
@@ -351,6 +364,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     if (p.n_points) memcpy(h + o_pts[b], p.points_xy, (size_t)p.n_points * 16);
     if (conf && p.rand_stream) memcpy(h + o_rnd[b], p.rand_stream, (size_t)prm.n_draws * 4);
     need = std::max(need, p.n_points * 16 + map_dyn[map_of[b]]);
+    bt->max_pts = std::max(bt->max_pts, p.n_points);
   }
   bt->need_dyn_smem = need;
   if (extra_upload_off) *extra_upload_off = o_extra_up;
@@ -391,6 +405,67 @@ int launch_pso(ndtpso_batch* bt, int smem) {
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   return NDTPSO_OK;
+}
+
+// Point-sliced kernel: T = 32*NW threads hold NPT scan points each and score JB candidates at a
+// time.  launch_sliced returns 1 when the batch does not qualify (table too large for shared
+// memory, scan too long, > 65534 built cells).
+template <int NPT, int JB, int MAXT, int MINB>
+int launch_sliced_cfg(ndtpso_batch* bt, int nw, int smem) {
+  ndtpso_ctx* ctx = bt->ctx;
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(pso_sliced_kernel<NPT, JB, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ctx->max_smem_optin));
+    attr_set[ctx->device & 63] = true;
+  }
+  PsoParams prm = bt->prm;
+  prm.smem_bytes = smem;
+  pso_sliced_kernel<NPT, JB, MAXT, MINB><<<bt->n, nw * 32, smem, ctx->stream>>>(bt->d_probs, bt->d_maps, prm, bt->d_out, bt->d_stats);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return NDTPSO_OK;
+}
+
+// maximum warps per CTA of each points-per-thread variant (its __launch_bounds__)
+constexpr int kSlicedMaxWarps[kSlicedMaxNPT + 1] = {0, 20, 20, 12, 10, 8, 8};
+
+int launch_sliced(ndtpso_batch* bt) {
+  ndtpso_ctx* ctx = bt->ctx;
+  if (!bt->all_compact || !bt->all_symmetric) return 1;
+  const int n = std::max(bt->max_pts, 1);
+  int npt = 0, nw = 0;
+  if (ctx->opt_npt > 0) {
+    npt = std::min(ctx->opt_npt, kSlicedMaxNPT);
+    nw = (n + 32 * npt - 1) / (32 * npt);
+  } else if (ctx->opt_warps > 0) {
+    npt = (n + 32 * ctx->opt_warps - 1) / (32 * ctx->opt_warps);
+    if (npt > kSlicedMaxNPT) return 1;
+    nw = (n + 32 * npt - 1) / (32 * npt);
+  } else {
+    // default: about 12 warps per CTA (two CTAs per SM at <= 80 registers measured fastest, see
+    // profiles/r01_phaseB_microbench.md): the fewest points per thread that needs at most 12 warps
+    for (npt = 1; npt <= kSlicedMaxNPT; ++npt) {
+      nw = (n + 32 * npt - 1) / (32 * npt);
+      if (nw <= 12) break;
+    }
+    if (npt > kSlicedMaxNPT) return 1;
+  }
+  if (npt < 1 || npt > kSlicedMaxNPT || nw > kSlicedMaxWarps[npt]) return 1;
+  nw = std::max(nw, 4);
+  const int smem = round16(sliced_smem_bytes(bt->prm.P, nw, bt->max_table_smem));
+  if (smem > ctx->max_smem_optin) return 1;
+  const int jb = ctx->opt_cand_batch;
+  switch (npt) {
+    case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 640, 1>(bt, nw, smem) : jb == 2 ? launch_sliced_cfg<1, 2, 640, 1>(bt, nw, smem)
+                                                                                     : launch_sliced_cfg<1, 4, 640, 1>(bt, nw, smem);
+    case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 640, 1>(bt, nw, smem) : jb == 2 ? launch_sliced_cfg<2, 2, 640, 1>(bt, nw, smem)
+                                                                                     : launch_sliced_cfg<2, 4, 640, 1>(bt, nw, smem);
+    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 384, 2>(bt, nw, smem) : launch_sliced_cfg<3, 2, 384, 2>(bt, nw, smem);
+    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 320, 2>(bt, nw, smem) : launch_sliced_cfg<4, 2, 320, 2>(bt, nw, smem);
+    case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 256, 2>(bt, nw, smem) : launch_sliced_cfg<5, 2, 256, 2>(bt, nw, smem);
+    default: return jb == 1 ? launch_sliced_cfg<6, 1, 256, 2>(bt, nw, smem) : launch_sliced_cfg<6, 2, 256, 2>(bt, nw, smem);
+  }
 }
 
 int launch_compact(ndtpso_batch* bt) {
@@ -484,8 +559,20 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
   if (!ctx) return NDTPSO_ERR_ARG;
   switch (option) {
     case NDTPSO_OPT_WARPS_PER_CTA:
-      if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) return fail(ctx, NDTPSO_ERR_ARG, "warps per CTA must be 0, 4, 8, 16 or 32");
+      if (value < 0 || value > 32) return fail(ctx, NDTPSO_ERR_ARG, "warps per CTA must be in 0..32");
       ctx->opt_warps = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_KERNEL:
+      if (value < 0 || value > 2) return fail(ctx, NDTPSO_ERR_ARG, "kernel must be 0 (auto), 1 (warp-per-particle) or 2 (point-sliced)");
+      ctx->opt_kernel = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_CANDIDATE_BATCH:
+      if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NDTPSO_ERR_ARG, "candidate batch must be 0, 1, 2 or 4");
+      ctx->opt_cand_batch = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_POINTS_PER_THREAD:
+      if (value < 0 || value > kSlicedMaxNPT) return fail(ctx, NDTPSO_ERR_ARG, "points per thread out of range");
+      ctx->opt_npt = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_SMEM_BYTES:
       if (value < 0 || value > ctx->max_smem_optin) return fail(ctx, NDTPSO_ERR_ARG, "shared memory bytes out of range");
@@ -527,7 +614,10 @@ int ndtpso_batch_solve(ndtpso_batch* bt) {
   if (!bt || !bt->has_pso) return NDTPSO_ERR_ARG;
   ndtpso_ctx* ctx = bt->ctx;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (bt->n == 0) return NDTPSO_OK;
+  if (bt->n == 0) {
+    bt->solved = true;
+    return NDTPSO_OK;
+  }
   if (!bt->ev[0])
     for (auto& e : bt->ev) CUDA_TRY(ctx, cudaEventCreate(&e));
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[0], ctx->stream));
@@ -540,13 +630,17 @@ int ndtpso_batch_solve(ndtpso_batch* bt) {
     ctx->launches++;
   }
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[2], ctx->stream));
-  const int fixed = pso_fixed_smem_bytes(bt->prm.P);
-  const int smem = pick_smem(ctx, fixed, bt->need_dyn_smem);
-  switch (pick_warps(ctx)) {
-    case 4: rc = launch_pso<4>(bt, smem); break;
-    case 16: rc = launch_pso<16>(bt, smem); break;
-    case 32: rc = launch_pso<32>(bt, smem); break;
-    default: rc = launch_pso<8>(bt, smem); break;
+  rc = ctx->opt_kernel == 1 ? 1 : launch_sliced(bt);
+  if (rc == 1) {  // generic warp-per-particle kernel: any scan length, any table size
+    if (ctx->opt_kernel == 2) return fail(ctx, NDTPSO_ERR_LIMIT, "batch does not qualify for the point-sliced kernel");
+    const int fixed = pso_fixed_smem_bytes(bt->prm.P);
+    const int smem = pick_smem(ctx, fixed, bt->need_dyn_smem);
+    switch (pick_warps(ctx)) {
+      case 4: rc = launch_pso<4>(bt, smem); break;
+      case 16: rc = launch_pso<16>(bt, smem); break;
+      case 32: rc = launch_pso<32>(bt, smem); break;
+      default: rc = launch_pso<8>(bt, smem); break;
+    }
   }
   if (rc) return rc;
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[3], ctx->stream));
@@ -643,7 +737,7 @@ int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems
   rc = launch_compact(bt);
   if (rc) return cleanup(rc);
   constexpr int NW = 8;
-  const int smem = pick_smem(ctx, 16, bt->need_dyn_smem);
+  const int smem = pick_smem(ctx, kCostFixedSmem, bt->need_dyn_smem);
   cudaError_t e = cudaFuncSetAttribute(cost_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
   unsigned char* d = static_cast<unsigned char*>(bt->dev.ptr);

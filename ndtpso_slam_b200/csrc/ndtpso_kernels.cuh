@@ -1,8 +1,8 @@
 // Device side of the B200-native PSO/NDT scan matcher (sm_100a).
 //
 // Kernels (one launch each per batch):
-//   compact_map_kernel  K0  dense/sparse (mu, Sigma^-1, built) table -> u16 lookup grid over the
-//                           bounding box of the built cells + packed 48-byte records
+//   compact_map_kernel  K0  dense/sparse (mu, Sigma^-1, built) table -> u16 row-strip lookup grid
+//                           + packed 48-byte records {mu, -Sigma^-1/2}
 //   rng_fill_kernel     K1  glibc TYPE_3 rand() stream of srand(seed), 32 values per warp step
 //   pso_kernel          K2  the hot path: P+1+P*I NDT cost evaluations and the swarm update with
 //                           the reference's SEQUENTIAL gbest order (speculate-and-replay)
@@ -20,19 +20,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fast_exp.h"
+
 namespace ndtpso {
 
 // ------------------------------------------------------------------------------------------
 // Device-resident descriptors (built on the host, one H2D with the rest of the batch)
 // ------------------------------------------------------------------------------------------
-enum { HDR_NREC = 0, HDR_BX0, HDR_BY0, HDR_BW, HDR_BH, HDR_MODE, HDR_WORDS = 8 };
+enum { HDR_NREC = 0, HDR_ROW0, HDR_NROWS, HDR_MODE, HDR_WORDS = 4 };
 enum { MAP_COMPACT = 0, MAP_DENSE_DIRECT = 1 };  // hdr[HDR_MODE]
 
 struct DevMap {
   double x_min, x_max, y_min, y_max;
   double hw, hh;        // width/2., height/2. (ndtframe.cpp:245-246)
-  double cs, inv_cs;    // cell_side and, when cs is a power of two, its exact reciprocal
-  int gw, gh, ncells, cs_pow2;
+  double cs, inv_cs;    // cell_side and 1/cell_side (exact when cs is a power of two)
+  int gw, gh, ncells;
+  int fast_geom;        // 1: cs is a power of two and the bounds are symmetric (x_min == -x_max, y_min == -y_max)
   // input table (device pointers)
   const double* mean;      // [rows][2]
   const double* icov;      // [rows][4]
@@ -41,8 +44,8 @@ struct DevMap {
   int n_sparse;            // < 0: dense
   int _pad;
   // compact table written by K0
-  unsigned short* grid;    // capacity ncells (+ padding to 16 B)
-  double* rec;             // capacity rows*6: {mx, my, S00, S01, S10, S11}
+  unsigned short* grid;    // [nrows*gw + 1] record id per cell of rows row0..row0+nrows-1; last = null id
+  double* rec;             // [(n_rec + 1)][6]: {mx, my, -S00/2, -S01/2, -S10/2, -S11/2}; last = null record
   int* hdr;                // HDR_WORDS ints
 };
 
@@ -64,6 +67,10 @@ struct PsoParams {
   int smem_bytes;   // dynamic shared memory given to pso_kernel
 };
 
+__constant__ double c_exp_table[kExpTableSize] = {
+#include "exp_table.inc"
+};
+
 // ------------------------------------------------------------------------------------------
 // small PTX helpers: mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP)
 // ------------------------------------------------------------------------------------------
@@ -73,7 +80,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -97,13 +103,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
-__device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; }
+__host__ __device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; }
 
 // ------------------------------------------------------------------------------------------
 // K0: compact the NDT table.  One CTA per map.
-//   pass A: count built cells per thread chunk + bounding box -> block scan
-//   pass B: fill the bbox grid with 0xFFFF, then write record slots and packed records
-// Record order = ascending cell index (deterministic).
+//   pass A: count built cells per thread chunk + first/last occupied grid row -> block scan
+//   pass B: fill the row strip with the null id, then write record ids and packed records
+// Record order = ascending cell index (deterministic).  The grid covers whole rows
+// row0..row0+nrows-1 so that the reference's FLAT index ix + gw*iy (including its wrap into the
+// next row when (x + W/2)/cs rounds up to gw, ndtframe.cpp:245) addresses it directly.
 // ------------------------------------------------------------------------------------------
 constexpr int K0_THREADS = 256;
 
@@ -116,16 +124,14 @@ __global__ void __launch_bounds__(K0_THREADS) compact_map_kernel(const DevMap* _
   const int lo = min(rows, tid * chunk), hi = min(rows, lo + chunk);
 
   __shared__ int s_scan[K0_THREADS];
-  __shared__ int s_box[4];
+  __shared__ int s_box[2];
   if (tid == 0) {
-    s_box[0] = INT_MAX;  // min ix
-    s_box[1] = INT_MAX;  // min iy
-    s_box[2] = -1;       // max ix
-    s_box[3] = -1;       // max iy
+    s_box[0] = INT_MAX;  // min iy
+    s_box[1] = -1;       // max iy
   }
   __syncthreads();
 
-  int cnt = 0, ax = INT_MAX, ay = INT_MAX, bx = -1, by = -1;
+  int cnt = 0, ay = INT_MAX, by = -1;
   for (int r = lo; r < hi; ++r) {
     int cell;
     if (sparse) {
@@ -134,18 +140,14 @@ __global__ void __launch_bounds__(K0_THREADS) compact_map_kernel(const DevMap* _
       if (!m.built[r]) continue;
       cell = r;
     }
-    const int ix = cell % m.gw, iy = cell / m.gw;
-    ax = min(ax, ix);
+    const int iy = cell / m.gw;
     ay = min(ay, iy);
-    bx = max(bx, ix);
     by = max(by, iy);
     ++cnt;
   }
   if (cnt) {
-    atomicMin(&s_box[0], ax);
-    atomicMin(&s_box[1], ay);
-    atomicMax(&s_box[2], bx);
-    atomicMax(&s_box[3], by);
+    atomicMin(&s_box[0], ay);
+    atomicMax(&s_box[1], by);
   }
   s_scan[tid] = cnt;
   __syncthreads();
@@ -158,22 +160,24 @@ __global__ void __launch_bounds__(K0_THREADS) compact_map_kernel(const DevMap* _
   const int n_rec = s_scan[K0_THREADS - 1];
   int slot = s_scan[tid] - cnt;  // exclusive prefix
 
-  const int bx0 = n_rec ? s_box[0] : 0, by0 = n_rec ? s_box[1] : 0;
-  const int bw = n_rec ? s_box[2] - s_box[0] + 1 : 0, bh = n_rec ? s_box[3] - s_box[1] + 1 : 0;
+  const int row0 = n_rec ? s_box[0] : 0;
+  const int nrows = n_rec ? s_box[1] - s_box[0] + 1 : 0;
   const bool compact_ok = n_rec <= 65534;
   if (tid == 0) {
     m.hdr[HDR_NREC] = n_rec;
-    m.hdr[HDR_BX0] = bx0;
-    m.hdr[HDR_BY0] = by0;
-    m.hdr[HDR_BW] = bw;
-    m.hdr[HDR_BH] = bh;
+    m.hdr[HDR_ROW0] = row0;
+    m.hdr[HDR_NROWS] = nrows;
     m.hdr[HDR_MODE] = compact_ok ? MAP_COMPACT : MAP_DENSE_DIRECT;
   }
   if (!compact_ok) return;  // uniform: the hot kernel reads the dense arrays directly
 
-  for (int g = tid; g < bw * bh; g += K0_THREADS) m.grid[g] = 0xFFFFu;
+  const int span = nrows * m.gw;
+  const unsigned short null_id = static_cast<unsigned short>(n_rec);
+  for (int g = tid; g <= span; g += K0_THREADS) m.grid[g] = null_id;
+  if (tid < 6) m.rec[6 * (size_t)n_rec + tid] = 0.;  // null record (never contributes; keeps loads in range)
   __syncthreads();
 
+  const int base = row0 * m.gw;
   for (int r = lo; r < hi; ++r) {
     int cell;
     if (sparse) {
@@ -182,15 +186,15 @@ __global__ void __launch_bounds__(K0_THREADS) compact_map_kernel(const DevMap* _
       if (!m.built[r]) continue;
       cell = r;
     }
-    const int ix = cell % m.gw, iy = cell / m.gw;
-    m.grid[(iy - by0) * bw + (ix - bx0)] = static_cast<unsigned short>(slot);
+    m.grid[cell - base] = static_cast<unsigned short>(slot);
     double* rec = m.rec + 6 * (size_t)slot;
     const double2 mu = *reinterpret_cast<const double2*>(m.mean + 2 * (size_t)r);
     const double2 s0 = *reinterpret_cast<const double2*>(m.icov + 4 * (size_t)r);
     const double2 s1 = *reinterpret_cast<const double2*>(m.icov + 4 * (size_t)r + 2);
+    // -S/2 is an exact scaling: -(d'Sd)/2 (ndtcell.cpp:74-75) == d'(-S/2)d bit for bit
     *reinterpret_cast<double2*>(rec) = mu;
-    *reinterpret_cast<double2*>(rec + 2) = s0;
-    *reinterpret_cast<double2*>(rec + 4) = s1;
+    *reinterpret_cast<double2*>(rec + 2) = make_double2(-0.5 * s0.x, -0.5 * s0.y);
+    *reinterpret_cast<double2*>(rec + 4) = make_double2(-0.5 * s1.x, -0.5 * s1.y);
     ++slot;
   }
 }
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
     v += 165u * (z[(n - 117) & (K1_RING - 1)] + z[(n - 257) & (K1_RING - 1)]);
     v += 330u * (z[(n - 145) & (K1_RING - 1)] + z[(n - 229) & (K1_RING - 1)]);
     v += 462u * (z[(n - 173) & (K1_RING - 1)] + z[(n - 201) & (K1_RING - 1)]);
-    __syncwarp();  // all reads of the slots about to be overwritten are done
+    __syncwarp();
     z[n & (K1_RING - 1)] = v;
     const int k = n - 341;
     if (k < n_draws) out[k] = static_cast<int>(v >> 1);
@@ -258,87 +262,150 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
 // ------------------------------------------------------------------------------------------
 // NDT cost of one candidate pose, evaluated by one warp (lanes stride over the points).
 // ------------------------------------------------------------------------------------------
-enum { TABLE_SMEM = 0, TABLE_GLOBAL = 1, TABLE_DENSE = 2 };
-
-struct MapCtx {
-  double x_min, x_max, y_min, y_max, hw, hh, cs, inv_cs;
-  int gw, ncells;
-  int bx0, by0, bw, bh;
-  const unsigned short* grid;  // TABLE_SMEM / TABLE_GLOBAL
-  const double* rec;           // TABLE_SMEM / TABLE_GLOBAL
-  const double* mean;          // TABLE_DENSE
-  const double* icov;
-  const uint8_t* built;
-};
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;  // identical in every lane; fixed butterfly order => deterministic
 }
 
-template <int TABLE, bool POW2>
-__device__ __forceinline__ double warp_cost(const MapCtx& m, const double2* __restrict__ pts, int n, double tx, double ty, double th,
-                                            int lane) {
-  double s, c;
-  sincos(th, &s, &c);
-  double acc = 0.;
-#pragma unroll 2
-  for (int i = lane; i < n; i += 32) {
+// ---- fast path: table staged in shared memory, branch-free, custom exp -------------------
+// FAST_GEOM = cell side a power of two and symmetric bounds (every frame the reference builds,
+// ndtframe.cpp:57-65, with cell sides 0.25/0.5/1/2): bounds test |x| < x_max, cell coordinate
+// fma(x, 1/cs, (W/2)/cs) (bit-identical to (x + W/2)/cs because scaling by 2^k is exact).
+// Otherwise: four strict compares and a true IEEE division.
+struct FastCost {
+  const double2* pts;          // shared
+  const unsigned short* grid;  // shared, [span + 1]
+  const double* rec;           // shared, [(n_rec + 1) * 6]
+  const double* etab;          // shared, [64]
+  double x_min, x_max, y_min, y_max;
+  double hw, hh, cs, inv_cs, hw_s, hh_s;  // hw_s = hw * inv_cs
+  int n, gw, base, span, null_id;
+
+  template <bool FAST_GEOM>
+  __device__ __forceinline__ double point(int i, double c, double s, double tx, double ty) const {
     const double2 p = pts[i];
-    const double x = p.x * c - p.y * s + tx;  // transform_point, core.h:29-30
-    const double y = p.x * s + p.y * c + ty;
-    if ((x > m.x_min) && (x < m.x_max) && (y > m.y_min) && (y < m.y_max)) {  // strict, ndtframe.cpp:242
-      const double fx = floor(POW2 ? (x + m.hw) * m.inv_cs : (x + m.hw) / m.cs);
-      const double fy = floor(POW2 ? (y + m.hh) * m.inv_cs : (y + m.hh) / m.cs);
-      int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
-      if (ix >= m.gw) {  // (x + W/2)/cs rounded up to gw: the reference's flat index wraps into the next row
-        ix -= m.gw;
-        iy += 1;
-      }
-      const double* rec = nullptr;
-      double mx, my, s00, s01, s10, s11;
-      bool hit = false;
-      if (TABLE == TABLE_DENSE) {
-        const int idx = ix + m.gw * iy;
-        if (idx < m.ncells && m.built[idx]) {
-          hit = true;
-          mx = m.mean[2 * idx];
-          my = m.mean[2 * idx + 1];
-          s00 = m.icov[4 * idx];
-          s01 = m.icov[4 * idx + 1];
-          s10 = m.icov[4 * idx + 2];
-          s11 = m.icov[4 * idx + 3];
-        }
-      } else {
-        const unsigned gx = static_cast<unsigned>(ix - m.bx0), gy = static_cast<unsigned>(iy - m.by0);
-        if (gx < static_cast<unsigned>(m.bw) && gy < static_cast<unsigned>(m.bh)) {
-          const unsigned r = m.grid[gy * m.bw + gx];
-          if (r != 0xFFFFu) {
-            hit = true;
-            rec = m.rec + 6 * r;
-            const double2 a = *reinterpret_cast<const double2*>(rec);
-            const double2 b = *reinterpret_cast<const double2*>(rec + 2);
-            const double2 d = *reinterpret_cast<const double2*>(rec + 4);
-            mx = a.x;
-            my = a.y;
-            s00 = b.x;
-            s01 = b.y;
-            s10 = d.x;
-            s11 = d.y;
-          }
-        }
-      }
-      if (hit) {  // normalDistribution, ndtcell.cpp:72-75
-        const double d0 = x - mx, d1 = y - my;
-        const double r0 = d0 * s00 + d1 * s10;
-        const double r1 = d0 * s01 + d1 * s11;
-        acc -= exp(-(r0 * d0 + r1 * d1) / 2.);
-      }
+    const double x = fma(p.x, c, fma(-p.y, s, tx));  // transform_point, core.h:29-30
+    const double y = fma(p.x, s, fma(p.y, c, ty));
+    bool inb;
+    double u, v;
+    if (FAST_GEOM) {
+      inb = (fabs(x) < x_max) && (fabs(y) < y_max);  // strict, ndtframe.cpp:242
+      u = fma(x, inv_cs, hw_s);
+      v = fma(y, inv_cs, hh_s);
+    } else {
+      inb = (x > x_min) && (x < x_max) && (y > y_min) && (y < y_max);
+      u = __ddiv_rn(x + hw, cs);
+      v = __ddiv_rn(y + hh, cs);
     }
+    const int ix = __double2int_rd(u), iy = __double2int_rd(v);  // floor, ndtframe.cpp:245-246
+    const unsigned g = static_cast<unsigned>(ix + gw * iy - base);
+    const bool in_strip = inb && (g < static_cast<unsigned>(span));
+    const unsigned r = grid[in_strip ? g : static_cast<unsigned>(span)];
+    const double* q = rec + 6 * r;
+    const double2 mu = *reinterpret_cast<const double2*>(q);
+    const double2 h0 = *reinterpret_cast<const double2*>(q + 2);
+    const double2 h1 = *reinterpret_cast<const double2*>(q + 4);
+    const double d0 = x - mu.x, d1 = y - mu.y;  // normalDistribution, ndtcell.cpp:72-75
+    const double r0 = fma(d1, h1.x, d0 * h0.x);
+    const double r1 = fma(d1, h1.y, d0 * h0.y);
+    const double a = fma(r1, d1, r0 * d0);       // = -(d' S d)/2
+    const double e = fast_exp(a, etab);
+    return (in_strip && r != static_cast<unsigned>(null_id)) ? e : 0.0;
   }
-  return warp_sum(acc);
-}
+
+  template <bool FAST_GEOM>
+  __device__ __forceinline__ double eval(double tx, double ty, double th, int lane) const {
+    double s, c;
+    sincos(th, &s, &c);
+    double acc0 = 0., acc1 = 0.;
+    int i = lane;
+    for (; i + 32 < n; i += 64) {
+      const double e0 = point<FAST_GEOM>(i, c, s, tx, ty);
+      const double e1 = point<FAST_GEOM>(i + 32, c, s, tx, ty);
+      acc0 -= e0;
+      acc1 -= e1;
+    }
+    if (i < n) acc0 -= point<FAST_GEOM>(i, c, s, tx, ty);
+    return warp_sum(acc0 + acc1);
+  }
+};
+
+// ---- fallback: table (and possibly points) in global memory; library exp --------------------
+// Used when the compact table does not fit the CTA's shared memory or has more than 65534 built
+// cells (then it reads the caller's dense arrays directly).
+struct SlowCost {
+  const double2* pts;  // generic
+  double x_min, x_max, y_min, y_max, hw, hh, cs;
+  int n, gw, ncells, base, span, null_id;
+  bool dense;
+  const unsigned short* grid;
+  const double* rec;
+  const double* mean;
+  const double* icov;
+  const uint8_t* built;
+
+  __device__ __forceinline__ double eval(double tx, double ty, double th, int lane) const {
+    double s, c;
+    sincos(th, &s, &c);
+    double acc = 0.;
+    for (int i = lane; i < n; i += 32) {
+      const double2 p = pts[i];
+      const double x = fma(p.x, c, fma(-p.y, s, tx));
+      const double y = fma(p.x, s, fma(p.y, c, ty));
+      if (!((x > x_min) && (x < x_max) && (y > y_min) && (y < y_max))) continue;
+      const int ix = __double2int_rd(__ddiv_rn(x + hw, cs)), iy = __double2int_rd(__ddiv_rn(y + hh, cs));
+      const int idx = ix + gw * iy;
+      double mx, my, h00, h01, h10, h11;
+      if (dense) {
+        if (idx < 0 || idx >= ncells || !built[idx]) continue;
+        mx = mean[2 * idx];
+        my = mean[2 * idx + 1];
+        h00 = -0.5 * icov[4 * idx];
+        h01 = -0.5 * icov[4 * idx + 1];
+        h10 = -0.5 * icov[4 * idx + 2];
+        h11 = -0.5 * icov[4 * idx + 3];
+      } else {
+        const unsigned g = static_cast<unsigned>(idx - base);
+        if (g >= static_cast<unsigned>(span)) continue;
+        const unsigned r = grid[g];
+        if (r == static_cast<unsigned>(null_id)) continue;
+        const double* q = rec + 6 * r;
+        mx = q[0];
+        my = q[1];
+        h00 = q[2];
+        h01 = q[3];
+        h10 = q[4];
+        h11 = q[5];
+      }
+      const double d0 = x - mx, d1 = y - my;
+      const double r0 = fma(d1, h10, d0 * h00);
+      const double r1 = fma(d1, h11, d0 * h01);
+      acc -= exp(fma(r1, d1, r0 * d0));
+    }
+    return warp_sum(acc);
+  }
+};
+
+enum { COST_FAST_GEOM = 0, COST_FAST_ANY = 1, COST_SLOW = 2 };
+
+template <int MODE>
+struct CostOf;
+template <>
+struct CostOf<COST_FAST_GEOM> {
+  const FastCost& f;
+  __device__ __forceinline__ double operator()(double tx, double ty, double th, int lane) const { return f.eval<true>(tx, ty, th, lane); }
+};
+template <>
+struct CostOf<COST_FAST_ANY> {
+  const FastCost& f;
+  __device__ __forceinline__ double operator()(double tx, double ty, double th, int lane) const { return f.eval<false>(tx, ty, th, lane); }
+};
+template <>
+struct CostOf<COST_SLOW> {
+  const SlowCost& f;
+  __device__ __forceinline__ double operator()(double tx, double ty, double th, int lane) const { return f.eval(tx, ty, th, lane); }
+};
 
 // Eigen Random(): x + (y-x)*Scalar(rand())/Scalar(RAND_MAX) with x=-1, y=1; no fusion.
 __device__ __forceinline__ double unit_random(int r) {
@@ -352,6 +419,7 @@ struct __align__(16) Cand {
 // Shared-memory carve-up of pso_kernel (all offsets multiples of 16 bytes)
 struct PsoSmem {
   uint64_t* bar;
+  double* etab;   // [64]
   Cand* cand;     // [2][P+1]
   double* x;      // [P][3]
   double* v;      // [P][3]
@@ -363,8 +431,9 @@ struct PsoSmem {
 };
 
 __host__ __device__ inline int pso_fixed_smem_bytes(int P) {
-  int b = 16;                                  // mbarrier
-  b += 2 * (P + 1) * (int)sizeof(Cand);        // candidates, double buffered
+  int b = 16;                                       // mbarrier
+  b += kExpTableSize * (int)sizeof(double);         // exp table
+  b += 2 * (P + 1) * (int)sizeof(Cand);             // candidates, double buffered
   b += (P > 0 ? P : 1) * 13 * (int)sizeof(double);  // x, v, vnew, pb (3 each) + pbc
   return (b + 15) & ~15;
 }
@@ -373,8 +442,9 @@ __device__ __forceinline__ PsoSmem carve_smem(unsigned char* base, int P) {
   PsoSmem s;
   const int Pn = P > 0 ? P : 1;
   s.bar = reinterpret_cast<uint64_t*>(base);
-  s.cand = reinterpret_cast<Cand*>(base + 16);
-  double* d = reinterpret_cast<double*>(base + 16 + 2 * (P + 1) * sizeof(Cand));
+  s.etab = reinterpret_cast<double*>(base + 16);
+  s.cand = reinterpret_cast<Cand*>(base + 16 + kExpTableSize * sizeof(double));
+  double* d = reinterpret_cast<double*>(base + 16 + kExpTableSize * sizeof(double) + 2 * (P + 1) * sizeof(Cand));
   s.x = d;
   s.v = d + 3 * Pn;
   s.vnew = d + 6 * Pn;
@@ -395,9 +465,9 @@ __device__ __forceinline__ PsoSmem carve_smem(unsigned char* base, int P) {
 // gbest becomes j*'s candidate and the particles after j* are replayed against it.  Candidates are
 // double-buffered so one barrier per round suffices.
 // ------------------------------------------------------------------------------------------
-template <int TABLE, bool POW2, int NW>
-__device__ __forceinline__ void pso_body(const MapCtx& m, const double2* __restrict__ pts, int n_pts, const DevProblem& pr,
-                                         const PsoParams& prm, const PsoSmem& sm, double* __restrict__ out, int* __restrict__ stats) {
+template <class Cost, int NW>
+__device__ __forceinline__ void pso_body(const Cost& cost, const DevProblem& pr, const PsoParams& prm, const PsoSmem& sm,
+                                         double* __restrict__ out, int* __restrict__ stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = prm.P, I = prm.I;
   const int* __restrict__ rnd = pr.rnd;
@@ -413,10 +483,8 @@ __device__ __forceinline__ void pso_body(const MapCtx& m, const double2* __restr
       const double dv = seed_particle ? (k == 2 ? 1E-5 : 1E-4) : pr.dev[k];
       pos[k] = __dadd_rn(pr.guess[k], __dmul_rn(unit_random(rnd[3 * t + k]), dv));
     }
-    const double c = warp_cost<TABLE, POW2>(m, pts, n_pts, pos[0], pos[1], pos[2], lane);
-    if (lane == 0) {
-      cand0[t] = Cand{c, pos[0], pos[1], pos[2]};
-    }
+    const double c = cost(pos[0], pos[1], pos[2], lane);
+    if (lane == 0) cand0[t] = Cand{c, pos[0], pos[1], pos[2]};
   }
   __syncthreads();
   // every warp derives the initial gbest the way core.cpp:58-69 does (strict <, index order)
@@ -450,7 +518,7 @@ __device__ __forceinline__ void pso_body(const MapCtx& m, const double2* __restr
   while (it < I) {
     Cand* cand = par ? cand1 : cand0;
     // first pending particle owned by this warp
-    int j0 = start + ((warp - start) % NW + NW) % NW;
+    const int j0 = start + ((warp - start) % NW + NW) % NW;
     for (int j = j0; j < P; j += NW) {
       const int base = 3 + 3 * P + 6 * P * it + 6 * j;
       double u = 0.;
@@ -469,7 +537,7 @@ __device__ __forceinline__ void pso_body(const MapCtx& m, const double2* __restr
         nv[k] = __dadd_rn(__dadd_rn(t1, t2), t3);
         nx[k] = __dadd_rn(xk, nv[k]);  // core.cpp:89
       }
-      const double c = warp_cost<TABLE, POW2>(m, pts, n_pts, nx[0], nx[1], nx[2], lane);
+      const double c = cost(nx[0], nx[1], nx[2], lane);
       if (lane == 0) {
         cand[j] = Cand{c, nx[0], nx[1], nx[2]};
         sm.vnew[3 * j] = nv[0];
@@ -534,52 +602,31 @@ __device__ __forceinline__ void pso_body(const MapCtx& m, const double2* __restr
   }
 }
 
-// Stage one problem's points and compact table into shared memory with bulk TMA and pick the
-// table mode.  Returns the MapCtx and the points pointer the cost loop should use.
+// ------------------------------------------------------------------------------------------
+// Staging: points + compact table -> shared memory with bulk TMA; builds the cost evaluators.
+// ------------------------------------------------------------------------------------------
 struct Staged {
-  MapCtx m;
-  const double2* pts;  // global points (used when they do not fit in shared memory)
-  int table;           // TABLE_*
-  int pts_bytes, rec_bytes;
-  bool pts_fit;
+  FastCost fast;
+  SlowCost slow;
+  int mode;  // COST_*
 };
 
-__device__ __forceinline__ Staged stage_problem(const DevProblem& pr, const DevMap& mp, unsigned char* dyn, int dyn_bytes, uint64_t* bar) {
+// dyn: 16-byte aligned shared memory of dyn_bytes; etab: 64 doubles of shared memory
+__device__ __forceinline__ Staged stage_problem(const DevProblem& pr, const DevMap& mp, unsigned char* dyn, int dyn_bytes, double* etab,
+                                                uint64_t* bar) {
   Staged st;
-  MapCtx& m = st.m;
-  m.x_min = mp.x_min;
-  m.x_max = mp.x_max;
-  m.y_min = mp.y_min;
-  m.y_max = mp.y_max;
-  m.hw = mp.hw;
-  m.hh = mp.hh;
-  m.cs = mp.cs;
-  m.inv_cs = mp.inv_cs;
-  m.gw = mp.gw;
-  m.ncells = mp.ncells;
   const int n_rec = mp.hdr[HDR_NREC];
-  m.bx0 = mp.hdr[HDR_BX0];
-  m.by0 = mp.hdr[HDR_BY0];
-  m.bw = mp.hdr[HDR_BW];
-  m.bh = mp.hdr[HDR_BH];
+  const int row0 = mp.hdr[HDR_ROW0], nrows = mp.hdr[HDR_NROWS];
   const int mode = mp.hdr[HDR_MODE];
-  m.grid = mp.grid;
-  m.rec = mp.rec;
-  m.mean = mp.mean;
-  m.icov = mp.icov;
-  m.built = mp.built;
+  const int span = nrows * mp.gw, base = row0 * mp.gw;
 
   const int pts_bytes = pr.n_pts * 16;
-  const int rec_bytes = n_rec * 48;
-  const int grid_bytes = round16(m.bw * m.bh * 2);
+  const int rec_bytes = (n_rec + 1) * 48;
+  const int grid_bytes = round16((span + 1) * 2);
   const bool pts_fit = pts_bytes <= dyn_bytes;
   const bool table_fit = (mode == MAP_COMPACT) && (pts_bytes + rec_bytes + grid_bytes <= dyn_bytes);
-  st.table = (mode == MAP_COMPACT) ? (table_fit ? TABLE_SMEM : TABLE_GLOBAL) : TABLE_DENSE;
-  st.pts = pr.pts;
-  st.pts_bytes = pts_bytes;
-  st.rec_bytes = rec_bytes;
-  st.pts_fit = pts_fit;
 
+  if (threadIdx.x < kExpTableSize) etab[threadIdx.x] = c_exp_table[threadIdx.x];
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -592,21 +639,57 @@ __device__ __forceinline__ Staged stage_problem(const DevProblem& pr, const DevM
     if (threadIdx.x == 0) {
       mbar_expect_tx(bar, tx);
       if (pts_fit && pts_bytes) tma_load_1d(dyn, pr.pts, pts_bytes, bar);
-      if (table_fit && rec_bytes) tma_load_1d(dyn + pts_bytes, mp.rec, rec_bytes, bar);
-      if (table_fit && grid_bytes) tma_load_1d(dyn + pts_bytes + rec_bytes, mp.grid, grid_bytes, bar);
+      if (table_fit) tma_load_1d(dyn + pts_bytes, mp.rec, rec_bytes, bar);
+      if (table_fit) tma_load_1d(dyn + pts_bytes + rec_bytes, mp.grid, grid_bytes, bar);
     }
     mbar_wait(bar, 0);
   }
-  return st;
-}
 
-// Pointers into the staged copy, derived from the shared-memory base so that the compiler emits
-// LDS (not generic loads) in the TABLE_SMEM instantiation.
-__device__ __forceinline__ MapCtx smem_table(const Staged& st, const unsigned char* dyn) {
-  MapCtx m = st.m;
-  m.rec = reinterpret_cast<const double*>(dyn + st.pts_bytes);
-  m.grid = reinterpret_cast<const unsigned short*>(dyn + st.pts_bytes + st.rec_bytes);
-  return m;
+  FastCost& f = st.fast;
+  f.pts = reinterpret_cast<const double2*>(dyn);
+  f.rec = reinterpret_cast<const double*>(dyn + pts_bytes);
+  f.grid = reinterpret_cast<const unsigned short*>(dyn + pts_bytes + rec_bytes);
+  f.etab = etab;
+  f.x_min = mp.x_min;
+  f.x_max = mp.x_max;
+  f.y_min = mp.y_min;
+  f.y_max = mp.y_max;
+  f.hw = mp.hw;
+  f.hh = mp.hh;
+  f.cs = mp.cs;
+  f.inv_cs = mp.inv_cs;
+  f.hw_s = mp.hw * mp.inv_cs;
+  f.hh_s = mp.hh * mp.inv_cs;
+  f.n = pr.n_pts;
+  f.gw = mp.gw;
+  f.base = base;
+  f.span = span;
+  f.null_id = n_rec;
+
+  SlowCost& s = st.slow;
+  s.pts = pts_fit ? reinterpret_cast<const double2*>(dyn) : pr.pts;
+  s.x_min = mp.x_min;
+  s.x_max = mp.x_max;
+  s.y_min = mp.y_min;
+  s.y_max = mp.y_max;
+  s.hw = mp.hw;
+  s.hh = mp.hh;
+  s.cs = mp.cs;
+  s.n = pr.n_pts;
+  s.gw = mp.gw;
+  s.ncells = mp.ncells;
+  s.base = base;
+  s.span = span;
+  s.null_id = n_rec;
+  s.dense = (mode != MAP_COMPACT);
+  s.grid = mp.grid;
+  s.rec = mp.rec;
+  s.mean = mp.mean;
+  s.icov = mp.icov;
+  s.built = mp.built;
+
+  st.mode = table_fit ? (mp.fast_geom ? COST_FAST_GEOM : COST_FAST_ANY) : COST_SLOW;
+  return st;
 }
 
 template <int NW>
@@ -617,33 +700,19 @@ __global__ void __launch_bounds__(NW * 32) pso_kernel(const DevProblem* __restri
   const DevProblem& pr = probs[b];
   const DevMap& mp = maps[pr.map_id];
   PsoSmem sm = carve_smem(smem_raw, prm.P);
-  const Staged st = stage_problem(pr, mp, sm.dyn, prm.smem_bytes - sm.fixed_bytes, sm.bar);
+  const Staged st = stage_problem(pr, mp, sm.dyn, prm.smem_bytes - sm.fixed_bytes, sm.etab, sm.bar);
   double* o = out + 4 * (size_t)b;
   int* s = stats ? stats + 2 * (size_t)b : nullptr;
-  const bool pow2 = mp.cs_pow2 != 0;
-  if (st.table == TABLE_SMEM) {
-    const MapCtx m = smem_table(st, sm.dyn);
-    const double2* spts = reinterpret_cast<const double2*>(sm.dyn);
-    if (pow2)
-      pso_body<TABLE_SMEM, true, NW>(m, spts, pr.n_pts, pr, prm, sm, o, s);
-    else
-      pso_body<TABLE_SMEM, false, NW>(m, spts, pr.n_pts, pr, prm, sm, o, s);
+  if (st.mode == COST_FAST_GEOM) {
+    pso_body<CostOf<COST_FAST_GEOM>, NW>(CostOf<COST_FAST_GEOM>{st.fast}, pr, prm, sm, o, s);
+  } else if (st.mode == COST_FAST_ANY) {
+    pso_body<CostOf<COST_FAST_ANY>, NW>(CostOf<COST_FAST_ANY>{st.fast}, pr, prm, sm, o, s);
   } else {
-    // generic pointer: shared when the points fit, else global
-    const double2* gpts = st.pts_fit ? reinterpret_cast<const double2*>(sm.dyn) : st.pts;
-    if (st.table == TABLE_GLOBAL) {
-      if (pow2)
-        pso_body<TABLE_GLOBAL, true, NW>(st.m, gpts, pr.n_pts, pr, prm, sm, o, s);
-      else
-        pso_body<TABLE_GLOBAL, false, NW>(st.m, gpts, pr.n_pts, pr, prm, sm, o, s);
-    } else {
-      if (pow2)
-        pso_body<TABLE_DENSE, true, NW>(st.m, gpts, pr.n_pts, pr, prm, sm, o, s);
-      else
-        pso_body<TABLE_DENSE, false, NW>(st.m, gpts, pr.n_pts, pr, prm, sm, o, s);
-    }
+    pso_body<CostOf<COST_SLOW>, NW>(CostOf<COST_SLOW>{st.slow}, pr, prm, sm, o, s);
   }
 }
+
+constexpr int kCostFixedSmem = 16 + kExpTableSize * (int)sizeof(double);
 
 // cost_function alone: CTA per problem, warps stride over the candidate poses.
 template <int NW>
@@ -654,25 +723,18 @@ __global__ void __launch_bounds__(NW * 32) cost_kernel(const DevProblem* __restr
   const DevProblem& pr = probs[b];
   const DevMap& mp = maps[pr.map_id];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  unsigned char* dyn = smem_raw + 16;
-  const Staged st = stage_problem(pr, mp, dyn, smem_bytes - 16, bar);
+  double* etab = reinterpret_cast<double*>(smem_raw + 16);
+  const Staged st = stage_problem(pr, mp, smem_raw + kCostFixedSmem, smem_bytes - kCostFixedSmem, etab, bar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool pow2 = mp.cs_pow2 != 0;
-  const MapCtx ms = smem_table(st, dyn);
-  const double2* spts = reinterpret_cast<const double2*>(dyn);
-  const double2* gpts = st.pts_fit ? spts : st.pts;
   for (int q = warp; q < n_poses; q += NW) {
     const double* ps = poses + 3 * ((size_t)b * n_poses + q);
     double c;
-    if (st.table == TABLE_SMEM)
-      c = pow2 ? warp_cost<TABLE_SMEM, true>(ms, spts, pr.n_pts, ps[0], ps[1], ps[2], lane)
-               : warp_cost<TABLE_SMEM, false>(ms, spts, pr.n_pts, ps[0], ps[1], ps[2], lane);
-    else if (st.table == TABLE_GLOBAL)
-      c = pow2 ? warp_cost<TABLE_GLOBAL, true>(st.m, gpts, pr.n_pts, ps[0], ps[1], ps[2], lane)
-               : warp_cost<TABLE_GLOBAL, false>(st.m, gpts, pr.n_pts, ps[0], ps[1], ps[2], lane);
+    if (st.mode == COST_FAST_GEOM)
+      c = st.fast.eval<true>(ps[0], ps[1], ps[2], lane);
+    else if (st.mode == COST_FAST_ANY)
+      c = st.fast.eval<false>(ps[0], ps[1], ps[2], lane);
     else
-      c = pow2 ? warp_cost<TABLE_DENSE, true>(st.m, gpts, pr.n_pts, ps[0], ps[1], ps[2], lane)
-               : warp_cost<TABLE_DENSE, false>(st.m, gpts, pr.n_pts, ps[0], ps[1], ps[2], lane);
+      c = st.slow.eval(ps[0], ps[1], ps[2], lane);
     if (lane == 0) out[(size_t)b * n_poses + q] = c;
   }
 }

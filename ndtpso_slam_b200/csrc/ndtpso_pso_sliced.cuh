@@ -1,0 +1,544 @@
+// K2, point-sliced form: the production PSO kernel.
+//
+// One CTA per scan-match problem, T = 32*NW threads.  Thread t keeps scan points
+// t, t+T, t+2T, ... (NPT of them) in REGISTERS for the whole run; the compact NDT table
+// ({mu, -Sigma^-1/2} records + u16 row-strip grid) is staged once into shared memory by bulk TMA.
+// Every round has three phases:
+//   A  thread j owns particle j: velocity/position update from its private state and the current
+//      gbest (core.cpp:83-90, no FMA contraction), sincos of the candidate heading -> pose[j]
+//   -- barrier --
+//   B  every warp evaluates EVERY pending candidate on its own slice of the scan, JB candidates at
+//      a time (branch-free NDT score, fast_exp, JB*NPT independent evaluations in flight per lane),
+//      packed warp-shuffle reduction -> partial[j][warp]
+//   -- barrier --
+//   C  every warp sums the partials of the pending candidates (fixed order), finds j* = the first
+//      candidate that beats gbest (ballot), owners commit particles <= j* (core.cpp:89-105);
+//      particles after j* are replayed in the next round against the new gbest.
+// pose[] and partial[] are double buffered, particle state is private to its owner thread, so two
+// barriers per round suffice.  Work per warp in phase B is identical for every warp whatever the
+// number of pending candidates: no load imbalance, and replay rounds cost only what they recompute.
+#pragma once
+#include "ndtpso_kernels.cuh"
+
+namespace ndtpso {
+
+constexpr int kSlicedMaxNPT = 6;
+
+// Code-generation variants of the point evaluation (bit mask), selectable for measurement:
+enum {
+  VAR_FLOOR_ON_FP64 = 1,  // floor() by a round-down magic add on the fp64 pipe instead of F2I.F64.FLOOR (conversion pipe)
+  VAR_KF_ON_FP64 = 2,     // k as a double by subtracting the magic constant (fp64 pipe) instead of I2F.F64
+};
+constexpr int kProdVariant = 0;
+
+struct __align__(16) Pose {
+  double x, y, c, s, th, pad;  // {x, y} and {cos, sin} are the two 16-byte loads of phase B
+};
+
+// Shared memory: [mbarrier 16][exp table 128][exp constants 64][records][grid] at FIXED offsets
+// (so the hot loop's table addresses are a constant and one register), then the swarm arrays.
+constexpr int kSlicedTableOffset = 16 + (kExpTableSize + 8) * (int)sizeof(double);
+
+struct SlicedSmem {
+  uint64_t* bar;
+  double* etab;     // [16]
+  double* cst;      // [8] fast_exp constants
+  unsigned char* table;  // records, then grid
+  Pose* pose;       // [2][P+1]
+  double* partial;  // [2][(P+1)*NW]
+  double* cost0;    // [P+1] initial costs
+  double* x;        // [P][3]  owner-private particle state
+  double* v;        // [P][3]
+  double* vnew;     // [P][3]
+  double* pb;       // [P][3]
+  double* pbc;      // [P]
+};
+
+__host__ __device__ inline int sliced_swarm_smem_bytes(int P, int NW) {
+  const int Pn = P > 0 ? P : 1;
+  int b = 2 * (P + 1) * (int)sizeof(Pose);
+  b += 2 * (P + 1) * NW * (int)sizeof(double);
+  b += (P + 1) * (int)sizeof(double);
+  b += Pn * 13 * (int)sizeof(double);
+  return (b + 15) & ~15;
+}
+// total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2)
+__host__ __device__ inline int sliced_smem_bytes(int P, int NW, int table_bytes) {
+  return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, NW);
+}
+
+__device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int NW, int table_bytes) {
+  SlicedSmem s;
+  const int Pn = P > 0 ? P : 1;
+  s.bar = reinterpret_cast<uint64_t*>(base);
+  s.etab = reinterpret_cast<double*>(base + 16);
+  s.cst = s.etab + kExpTableSize;
+  s.table = base + kSlicedTableOffset;
+  unsigned char* p = s.table + table_bytes;
+  s.pose = reinterpret_cast<Pose*>(p);
+  p += 2 * (P + 1) * sizeof(Pose);
+  s.partial = reinterpret_cast<double*>(p);
+  p += 2 * (size_t)(P + 1) * NW * sizeof(double);
+  s.cost0 = reinterpret_cast<double*>(p);
+  p += (P + 1) * sizeof(double);
+  double* d = reinterpret_cast<double*>(p);
+  s.x = d;
+  s.v = d + 3 * Pn;
+  s.vnew = d + 6 * Pn;
+  s.pb = d + 9 * Pn;
+  s.pbc = d + 12 * Pn;
+  return s;
+}
+
+// Loop-invariant operands of the point evaluation, held in registers.
+struct SliceCtx {
+  const unsigned short* grid;  // shared
+  const double* rec;           // shared
+  const double* etab;          // shared
+  double x_min, x_max, y_min, y_max, hw, hh, cs, inv_cs, hw_s, hh_s;
+  double l2e, ln2hi, ln2lo, c7, c6, c5, c4, c3;  // fast_exp constants kept out of the immediate field
+  int gw, base, span, null_id;
+};
+
+// One scan point against one candidate pose: subtracts exp(-(d' S d)/2) from acc iff the point is
+// inside the frame (strict), its cell is built, and the value is a normal double (>= 2.2e-308;
+// smaller ones are flushed to zero, see fast_exp.h).  Padding points of the last slice are stored
+// as (1e200, 0): whatever the pose, |x'| or |y'| is then ~1e200, i.e. out of bounds, so they need
+// no validity flag.  `weird` is raised when the exponent is > 709, +inf or NaN -- only an indefinite
+// or non-finite "inverse covariance" can do that -- and the caller then re-scores the candidate
+// with slice_point_exact so that such inputs behave like the reference.
+template <bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, double tx, double ty, double c, double s, double& acc,
+                                            bool& weird) {
+  const double x = fma(p.x, c, fma(-p.y, s, tx));  // transform_point, core.h:29-30
+  const double y = fma(p.x, s, fma(p.y, c, ty));
+  bool inb;
+  double u, v;
+  if (FAST_GEOM) {
+    inb = (fabs(x) < m.x_max) && (fabs(y) < m.y_max);  // strict, ndtframe.cpp:242
+    u = fma(x, m.inv_cs, m.hw_s);                      // == (x + W/2)/cs exactly (cs = 2^k)
+    v = fma(y, m.inv_cs, m.hh_s);
+  } else {
+    inb = (x > m.x_min) && (x < m.x_max) && (y > m.y_min) && (y < m.y_max);
+    u = __ddiv_rn(x + m.hw, m.cs);
+    v = __ddiv_rn(y + m.hh, m.cs);
+  }
+  int ix, iy;  // floor, ndtframe.cpp:245-246
+  if (VAR & VAR_FLOOR_ON_FP64) {
+    ix = __double2loint(__dadd_rd(u, kExpMagic));  // valid for |u| < 2^31; out-of-range u only occurs out of bounds
+    iy = __double2loint(__dadd_rd(v, kExpMagic));
+  } else {
+    ix = __double2int_rd(u);
+    iy = __double2int_rd(v);
+  }
+  const unsigned g = static_cast<unsigned>(ix + m.gw * iy - m.base);
+  const bool in_strip = inb && (g < static_cast<unsigned>(m.span));
+  const unsigned r = m.grid[in_strip ? g : static_cast<unsigned>(m.span)];
+  const double* q = m.rec + 6 * r;
+  // the sliced kernel only runs on symmetric tables (S01 == S10 bit for bit, which is what
+  // NDTCell::s_calc_covar_inverse produces, ndtcell.cpp:109-110): 40 bytes per record instead of 48
+  const double2 mu = *reinterpret_cast<const double2*>(q);
+  const double2 h0 = *reinterpret_cast<const double2*>(q + 2);  // {-S00/2, -S01/2}
+  const double h11 = q[5];
+  const double d0 = x - mu.x, d1 = y - mu.y;  // normalDistribution, ndtcell.cpp:72-75
+  const double r0 = fma(d1, h0.y, d0 * h0.x);  // d0*S00 + d1*S10
+  const double r1 = fma(d1, h11, d0 * h0.y);   // d0*S01 + d1*S11
+  const double a = fma(r1, d1, r0 * d0);       // = -(d' S d)/2
+  // fast_exp (fast_exp.h), with its constants in registers
+  const double kd = fma(a, m.l2e, kExpMagic);
+  const int k = __double2loint(kd);
+  const double kf = (VAR & VAR_KF_ON_FP64) ? (kd - kExpMagic) : static_cast<double>(k);
+  double rr = fma(kf, m.ln2hi, a);
+  rr = fma(kf, m.ln2lo, rr);
+  double pl = fma(rr, m.c7, m.c6);
+  pl = fma(pl, rr, m.c5);
+  pl = fma(pl, rr, m.c4);
+  pl = fma(pl, rr, m.c3);
+  pl = fma(pl, rr, 0.5);
+  pl = fma(pl, rr, 1.0);
+  const double em1 = pl * rr;
+  const double t = m.etab[k & (kExpTableSize - 1)];
+  const double val = fma(t, em1, t);
+  const int ahi = __double2hiint(a);
+  // the result is a normal double for -708 <= a <= 709 (hi words of a: 0xC0862000 / 0x40862800)
+  const bool use = in_strip && (r != static_cast<unsigned>(m.null_id)) && (static_cast<unsigned>(ahi) <= 0xC0862000u);
+  const int ehi = use ? __double2hiint(val) + ((k >> kExpTableShift) << 20) : 0;
+  const int elo = use ? __double2loint(val) : 0;
+  acc -= __hiloint2double(ehi, elo);
+  weird = weird || (use && ahi > 0x40862800);
+}
+
+// Exact (library exp, branchy) version of the same point, for the rare `weird` candidates.
+__device__ __noinline__ double slice_point_exact(const SliceCtx& m, const double2 p, double tx, double ty, double c, double s) {
+  const double x = fma(p.x, c, fma(-p.y, s, tx));
+  const double y = fma(p.x, s, fma(p.y, c, ty));
+  if (!((x > m.x_min) && (x < m.x_max) && (y > m.y_min) && (y < m.y_max))) return 0.;
+  const int ix = __double2int_rd(__ddiv_rn(x + m.hw, m.cs)), iy = __double2int_rd(__ddiv_rn(y + m.hh, m.cs));
+  const unsigned g = static_cast<unsigned>(ix + m.gw * iy - m.base);
+  if (g >= static_cast<unsigned>(m.span)) return 0.;
+  const unsigned r = m.grid[g];
+  if (r == static_cast<unsigned>(m.null_id)) return 0.;
+  const double* q = m.rec + 6 * r;
+  const double d0 = x - q[0], d1 = y - q[1];
+  const double r0 = fma(d1, q[3], d0 * q[2]);
+  const double r1 = fma(d1, q[5], d0 * q[3]);
+  const double a = fma(r1, d1, r0 * d0);
+  return (a < -708.0) ? 0. : exp(a);
+}
+
+// Packed warp reduction of JB per-lane accumulators (one per candidate): after it, the total of
+// candidate packed_slot<JB>(lane) sits in every lane of its group.  JB candidates share the five
+// shuffle levels, so the cost is 5 + (JB - 1) exchanges instead of 5*JB, and the JB chains hide
+// each other's latency.  The tree is fixed => deterministic.
+template <int JB>
+__device__ __forceinline__ double packed_warp_sum(const double (&a)[JB], int lane);
+template <>
+__device__ __forceinline__ double packed_warp_sum<1>(const double (&a)[1], int) {
+  return warp_sum(a[0]);
+}
+template <>
+__device__ __forceinline__ double packed_warp_sum<2>(const double (&a)[2], int lane) {
+  const bool hi16 = (lane & 16) != 0;
+  double k = hi16 ? a[1] : a[0];
+  k += __shfl_xor_sync(0xffffffffu, hi16 ? a[0] : a[1], 16);  // lanes < 16: candidate 0, >= 16: candidate 1
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+  return k;
+}
+template <>
+__device__ __forceinline__ double packed_warp_sum<4>(const double (&a)[4], int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  double k01 = hi16 ? a[1] : a[0];
+  k01 += __shfl_xor_sync(0xffffffffu, hi16 ? a[0] : a[1], 16);
+  double k23 = hi16 ? a[3] : a[2];
+  k23 += __shfl_xor_sync(0xffffffffu, hi16 ? a[2] : a[3], 16);
+  double k = hi8 ? k23 : k01;
+  k += __shfl_xor_sync(0xffffffffu, hi8 ? k01 : k23, 8);  // bit 3 clear: candidates {0,1}; set: {2,3}
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+  return k;
+}
+template <int JB>
+__device__ __forceinline__ int packed_slot(int lane) {
+  if (JB == 1) return 0;
+  if (JB == 2) return (lane >> 4) & 1;
+  return ((lane >> 4) & 1) + ((lane >> 3) & 1) * 2;
+}
+template <int JB>
+__device__ __forceinline__ bool packed_writer(int lane) {
+  return JB == 4 ? (lane & 7) == 0 : JB == 2 ? (lane & 15) == 0 : lane == 0;
+}
+
+// phase B: this warp scores candidates [lo, hi) of `pose` on its slice of the scan, JB candidates
+// at a time.  The last batch is padded by re-scoring candidate hi-1; padding results are not stored.
+template <int NPT, int JB, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void score_candidates(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* part, int lo,
+                                                 int hi, int NW, int warp, int lane) {
+  for (int j = lo; j < hi; j += JB) {
+    double acc[JB];
+    double2 txy[JB], cs[JB];
+    bool weird = false;
+#pragma unroll
+    for (int b = 0; b < JB; ++b) {
+      const Pose* ps = pose + min(j + b, hi - 1);
+      txy[b] = *reinterpret_cast<const double2*>(&ps->x);
+      cs[b] = *reinterpret_cast<const double2*>(&ps->c);
+      acc[b] = 0.;
+    }
+#pragma unroll
+    for (int b = 0; b < JB; ++b) {
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b], weird);
+    }
+    if (__any_sync(0xffffffffu, weird)) {  // never taken for tables NDTCell::build can produce
+#pragma unroll
+      for (int b = 0; b < JB; ++b) {
+        acc[b] = 0.;
+#pragma unroll 1
+        for (int k = 0; k < NPT; ++k) acc[b] -= slice_point_exact(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y);
+      }
+    }
+    const double tot = packed_warp_sum<JB>(acc, lane);
+    const int jj = j + packed_slot<JB>(lane);
+    if (packed_writer<JB>(lane) && jj < hi) part[jj * NW + warp] = tot;
+  }
+}
+
+template <int NPT, int JB, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&pt)[NPT], const DevProblem& pr, const PsoParams& prm,
+                                            const SlicedSmem& sm, double* __restrict__ out, int* __restrict__ stats) {
+  const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int P = prm.P, I = prm.I;
+  const int* __restrict__ rnd = pr.rnd;
+  Pose* pose0 = sm.pose;
+  Pose* pose1 = sm.pose + (P + 1);
+  double* part0 = sm.partial;
+  double* part1 = sm.partial + (size_t)(P + 1) * NW;
+
+  // cost of candidate j = sum of its NW partials in warp order (identical in every thread that asks)
+  auto total = [&](const double* part, int j) {
+    double c = 0.;
+    for (int w = 0; w < NW; ++w) c += part[j * NW + w];
+    return c;
+  };
+
+  // ---- initial swarm: task 0 = the seed particle (core.cpp:53,58), task 1+j = particle j (core.cpp:60-61)
+  for (int t = tid; t < P + 1; t += T) {
+    double pos[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double dv = (t == 0) ? (k == 2 ? 1E-5 : 1E-4) : pr.dev[k];
+      pos[k] = __dadd_rn(pr.guess[k], __dmul_rn(unit_random(rnd[3 * t + k]), dv));
+    }
+    double s, c;
+    sincos(pos[2], &s, &c);
+    pose0[t] = Pose{pos[0], pos[1], c, s, pos[2], 0.};
+  }
+  __syncthreads();
+  score_candidates<NPT, JB, FAST_GEOM, VAR>(m, pt, pose0, part0, 0, P + 1, NW, warp, lane);
+  __syncthreads();
+  for (int t = tid; t < P + 1; t += T) sm.cost0[t] = total(part0, t);
+  __syncthreads();
+  // every thread derives the initial gbest the way core.cpp:58-69 does (strict <, index order)
+  double gbc = sm.cost0[0], gb0 = pose0[0].x, gb1 = pose0[0].y, gb2 = pose0[0].th;
+  for (int j = 0; j < P; ++j) {
+    const double cj = sm.cost0[1 + j];
+    if (cj < gbc) {
+      gbc = cj;
+      gb0 = pose0[1 + j].x;
+      gb1 = pose0[1 + j].y;
+      gb2 = pose0[1 + j].th;
+    }
+  }
+  for (int j = tid; j < P; j += T) {  // owner-private state
+    const Pose ps = pose0[1 + j];
+    sm.x[3 * j] = ps.x;
+    sm.x[3 * j + 1] = ps.y;
+    sm.x[3 * j + 2] = ps.th;
+    sm.pb[3 * j] = ps.x;
+    sm.pb[3 * j + 1] = ps.y;
+    sm.pb[3 * j + 2] = ps.th;
+    sm.v[3 * j] = sm.v[3 * j + 1] = sm.v[3 * j + 2] = 0.;
+    sm.pbc[j] = sm.cost0[1 + j];
+  }
+
+  // ---- iterations
+  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0;
+  double w = prm.w;
+  while (it < I) {
+    Pose* pose = par ? pose1 : pose0;
+    double* part = par ? part1 : part0;
+    // phase A: owners of the pending particles [start, P)
+    const int ja = start + ((tid - start) % T + T) % T;  // first pending particle owned by this thread
+    for (int j = ja; j < P; j += T) {
+      const int base = 3 + 3 * P + 6 * P * it + 6 * j;
+      double nx[3], nv[3];
+      const double gb[3] = {gb0, gb1, gb2};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double rx = fabs(unit_random(rnd[base + 2 * k]));  // Array2d::Random().abs(), core.cpp:84
+        const double ry = fabs(unit_random(rnd[base + 2 * k + 1]));
+        const double xk = sm.x[3 * j + k], vk = sm.v[3 * j + k], pbk = sm.pb[3 * j + k];
+        // core.cpp:85-87: ((w*v) + ((c1*rx)*(pb-x))) + ((c2*ry)*(gb-x)), no contraction
+        const double t1 = __dmul_rn(w, vk);
+        const double t2 = __dmul_rn(__dmul_rn(prm.c1, rx), __dadd_rn(pbk, -xk));
+        const double t3 = __dmul_rn(__dmul_rn(prm.c2, ry), __dadd_rn(gb[k], -xk));
+        nv[k] = __dadd_rn(__dadd_rn(t1, t2), t3);
+        nx[k] = __dadd_rn(xk, nv[k]);  // core.cpp:89
+      }
+      double s, c;
+      sincos(nx[2], &s, &c);
+      pose[j] = Pose{nx[0], nx[1], c, s, nx[2], 0.};
+      sm.vnew[3 * j] = nv[0];
+      sm.vnew[3 * j + 1] = nv[1];
+      sm.vnew[3 * j + 2] = nv[2];
+    }
+    __syncthreads();
+    score_candidates<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, part, start, P, NW, warp, lane);  // phase B
+    __syncthreads();
+    // phase C: j* = first pending particle that improves gbest (core.cpp:98)
+    int jstar = -1;
+    double cstar = 0.;
+    for (int base = start; base < P && jstar < 0; base += 32) {
+      const int j = base + lane;
+      const double cj = (j < P) ? total(part, j) : 0.;
+      const bool imp = (j < P) && (cj < gbc);
+      const unsigned mask = __ballot_sync(0xffffffffu, imp);
+      if (mask) {
+        const int src = __ffs(mask) - 1;
+        jstar = base + src;
+        cstar = __shfl_sync(0xffffffffu, cj, src);
+      }
+    }
+    const int end = (jstar >= 0) ? jstar + 1 : P;
+    for (int j = ja; j < end; j += T) {  // commit own particles in [start, end)  (core.cpp:89-96)
+      const Pose ps = pose[j];
+      const double cj = total(part, j);
+      sm.x[3 * j] = ps.x;
+      sm.x[3 * j + 1] = ps.y;
+      sm.x[3 * j + 2] = ps.th;
+      sm.v[3 * j] = sm.vnew[3 * j];
+      sm.v[3 * j + 1] = sm.vnew[3 * j + 1];
+      sm.v[3 * j + 2] = sm.vnew[3 * j + 2];
+      if (cj < sm.pbc[j]) {
+        sm.pbc[j] = cj;
+        sm.pb[3 * j] = ps.x;
+        sm.pb[3 * j + 1] = ps.y;
+        sm.pb[3 * j + 2] = ps.th;
+      }
+    }
+    if (jstar >= 0) {  // core.cpp:102-103
+      gbc = cstar;
+      gb0 = pose[jstar].x;
+      gb1 = pose[jstar].y;
+      gb2 = pose[jstar].th;
+      ++n_gb;
+    }
+    start = end;
+    if (start >= P) {
+      start = 0;
+      ++it;
+      w = __dmul_rn(w, prm.wd);  // core.cpp:108
+    }
+    par ^= 1;
+    ++rounds;
+  }
+
+  if (tid == 0) {
+    out[0] = gb0;
+    out[1] = gb1;
+    out[2] = gb2;
+    out[3] = gbc;
+    if (stats) {
+      stats[0] = rounds;
+      stats[1] = n_gb;
+    }
+  }
+}
+
+// Prologue shared by the production kernel and the phase-B microbenchmark: stages the compact
+// table with two bulk TMA copies, loads this thread's scan points into registers meanwhile
+// (coalesced 16-byte loads), and fills the loop-invariant context.
+template <int NPT>
+__device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, const DevProblem& pr, const DevMap& mp, int P, SliceCtx& m,
+                                                      double2 (&pt)[NPT]) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n_rec = mp.hdr[HDR_NREC];
+  const int row0 = mp.hdr[HDR_ROW0], nrows = mp.hdr[HDR_NROWS];
+  const int span = nrows * mp.gw;
+  const int rec_bytes = (n_rec + 1) * 48;
+  const int grid_bytes = round16((span + 1) * 2);
+  const SlicedSmem sm = carve_sliced(smem_raw, P, T >> 5, rec_bytes + grid_bytes);
+
+  if (tid < kExpTableSize) sm.etab[tid] = c_exp_table[tid];
+  // constants go through volatile shared memory so the compiler keeps them in registers instead of
+  // re-materialising 64-bit immediates inside the loop
+  volatile double* cst = reinterpret_cast<volatile double*>(sm.cst);
+  if (tid == 0) {
+    const ExpConsts ec = exp_consts();
+    cst[0] = ec.l2e;
+    cst[1] = -ec.hi;
+    cst[2] = -ec.lo;
+    cst[3] = ec.c7;
+    cst[4] = ec.c6;
+    cst[5] = ec.c5;
+    cst[6] = ec.c4;
+    cst[7] = ec.c3;
+    mbar_init(sm.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(sm.bar, rec_bytes + grid_bytes);
+    tma_load_1d(sm.table, mp.rec, rec_bytes, sm.bar);
+    tma_load_1d(sm.table + rec_bytes, mp.grid, grid_bytes, sm.bar);
+  }
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const int i = k * T + tid;
+    pt[k] = (i < pr.n_pts) ? pr.pts[i] : make_double2(1e200, 0.);  // padding: out of bounds for every pose
+  }
+  m.rec = reinterpret_cast<const double*>(sm.table);
+  m.grid = reinterpret_cast<const unsigned short*>(sm.table + rec_bytes);
+  m.etab = sm.etab;
+  m.x_min = mp.x_min;
+  m.x_max = mp.x_max;
+  m.y_min = mp.y_min;
+  m.y_max = mp.y_max;
+  m.hw = mp.hw;
+  m.hh = mp.hh;
+  m.cs = mp.cs;
+  m.inv_cs = mp.inv_cs;
+  m.hw_s = mp.hw * mp.inv_cs;
+  m.hh_s = mp.hh * mp.inv_cs;
+  m.l2e = cst[0];
+  m.ln2hi = cst[1];
+  m.ln2lo = cst[2];
+  m.c7 = cst[3];
+  m.c6 = cst[4];
+  m.c5 = cst[5];
+  m.c4 = cst[6];
+  m.c3 = cst[7];
+  m.gw = mp.gw;
+  m.base = row0 * mp.gw;
+  m.span = span;
+  m.null_id = n_rec;
+  mbar_wait(sm.bar, 0);
+  return sm;
+}
+
+// Host guarantees: every table is compact and symmetric and fits prm.smem_bytes; n_pts <= NPT * blockDim.x.
+template <int NPT, int JB, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem* __restrict__ probs, const DevMap* __restrict__ maps,
+                                                              PsoParams prm, double* __restrict__ out, int* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const DevProblem& pr = probs[b];
+  const DevMap& mp = maps[pr.map_id];
+  SliceCtx m;
+  double2 pt[NPT];
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, m, pt);
+  double* o = out + 4 * (size_t)b;
+  int* s = stats ? stats + 2 * (size_t)b : nullptr;
+  if (mp.fast_geom)
+    sliced_body<NPT, JB, true, kProdVariant>(m, pt, pr, prm, sm, o, s);
+  else
+    sliced_body<NPT, JB, false, kProdVariant>(m, pt, pr, prm, sm, o, s);
+}
+
+// Phase-B microbenchmark: every CTA stages problem blockIdx.x % n_problems and scores `ncand`
+// synthetic candidates around its guess `reps` times.  out[blockIdx.x] = a checksum.
+template <int NPT, int JB, int VAR, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) score_bench_kernel(const DevProblem* __restrict__ probs, const DevMap* __restrict__ maps,
+                                                               int n_problems, int ncand, int reps, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevProblem& pr = probs[blockIdx.x % n_problems];
+  const DevMap& mp = maps[pr.map_id];
+  SliceCtx m;
+  double2 pt[NPT];
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, ncand - 1, m, pt);
+  const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < ncand; j += T) {
+    const double th = pr.guess[2] + 1e-3 * (j % 17 - 8);
+    double s, c;
+    sincos(th, &s, &c);
+    sm.pose[j] = Pose{pr.guess[0] + 0.01 * (j % 13 - 6), pr.guess[1] + 0.01 * (j % 11 - 5), c, s, th, 0.};
+  }
+  __syncthreads();
+  for (int r = 0; r < reps; ++r) {
+    if (mp.fast_geom)
+      score_candidates<NPT, JB, true, VAR>(m, pt, sm.pose, sm.partial, 0, ncand, NW, warp, lane);
+    else
+      score_candidates<NPT, JB, false, VAR>(m, pt, sm.pose, sm.partial, 0, ncand, NW, warp, lane);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double c = 0.;
+    for (int j = 0; j < ncand; ++j)
+      for (int w = 0; w < NW; ++w) c += sm.partial[j * NW + w];
+    out[blockIdx.x] = c;
+  }
+}
+
+}  // namespace ndtpso

@@ -293,6 +293,7 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     clocks = sampler.stop()
+    h2d_bytes, d2h_bytes = ctx.last_transfer_bytes()  # what align_batch really moved over PCIe per step
     assert np.array_equal(ep, pose), "e2e and resident paths disagree"
 
     fp64_peak = ctx.fp64_peak_tflops()

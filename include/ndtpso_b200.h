@@ -154,6 +154,9 @@ int ndtpso_batch_kernel_times(ndtpso_batch* batch, double* out_ms /* [3] */);
 void ndtpso_batch_destroy(ndtpso_batch* batch);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t ndtpso_ctx_launch_count(const ndtpso_ctx* ctx);
+/* bytes copied host->device by the most recent upload and device->host by the most recent results
+ * read of this context (what bench.py reports as h2d/d2h bytes per step) */
+int ndtpso_ctx_last_transfer_bytes(const ndtpso_ctx* ctx, int64_t* h2d, int64_t* d2h);
 int ndtpso_ctx_synchronize(ndtpso_ctx* ctx);
 
 /* ---- device self-measurement (roofline denominators MEASURED_PEAKS.json lacks) --- */

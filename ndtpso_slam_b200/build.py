@@ -25,6 +25,36 @@ def nvcc() -> str:
     return exe
 
 
+SHIM = os.path.join(PKG, "shim")
+SHIM_LIB = os.path.join(LIB_DIR, "libndtpso_slam.so")
+SHIM_SOURCES = [os.path.join(SHIM, "src", f) for f in ("ndtcell.cpp", "ndtframe.cpp", "core.cpp", "frame_capi.cpp")]
+EIGEN_STANDIN = os.path.join(PKG, "..", "third_party", "eigen_standin")
+
+
+def eigen_include() -> str:
+    """A system Eigen if there is one, else the fixed-size stand-in (third_party/eigen_standin)."""
+    for root in ("/usr/include", "/usr/local/include"):
+        if os.path.exists(os.path.join(root, "eigen3", "Eigen", "Core")):
+            return root
+    return EIGEN_STANDIN
+
+
+def build_shim(force: bool = False) -> str:
+    """libndtpso_slam.so: the drop-in NDTFrame / pso_optimization host library (g++, no FMA contraction,
+    like the reference's build) linked against libndtpso_b200.so."""
+    deps = SHIM_SOURCES + [os.path.join(SHIM, "include", "ndtpso_slam", f) for f in ("config.h", "core.h", "ndtcell.h", "ndtframe.h")]
+    deps += [os.path.join(PKG, "..", "include", "ndtpso_frames.h"), LIB_PATH]
+    if not force and os.path.exists(SHIM_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_LIB) for d in deps if os.path.exists(d)):
+        return SHIM_LIB
+    cmd = ["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(SHIM, "include"),
+           "-I" + os.path.join(PKG, "..", "include"), "-I" + eigen_include(), "-o", SHIM_LIB] + SHIM_SOURCES
+    cmd += ["-L" + LIB_DIR, "-lndtpso_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return SHIM_LIB
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -34,6 +64,7 @@ def is_stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
+        build_shim()
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
@@ -42,6 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    build_shim(force=True)
     return LIB_PATH
 
 

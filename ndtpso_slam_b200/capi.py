@@ -22,7 +22,7 @@ EXPORTS = [
     "ndtpso_abi_version", "ndtpso_pso_config_default", "ndtpso_device_count", "ndtpso_ctx_create", "ndtpso_ctx_destroy",
     "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch",
     "ndtpso_cost_batch", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
-    "ndtpso_batch_stats", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
+    "ndtpso_batch_stats", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library(build_if_missing: bool = True):
     L.ndtpso_batch_destroy.restype = None
     L.ndtpso_ctx_launch_count.argtypes = [C.c_void_p]
     L.ndtpso_ctx_launch_count.restype = C.c_int64
+    L.ndtpso_ctx_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ndtpso_ctx_synchronize.argtypes = [C.c_void_p]
     L.ndtpso_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
@@ -243,6 +244,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.ndtpso_ctx_launch_count(self.h))
+
+    def last_transfer_bytes(self):
+        """(h2d, d2h) bytes of the most recent upload / results read."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.ndtpso_ctx_last_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def synchronize(self):
         self._check(self.lib.ndtpso_ctx_synchronize(self.h))

@@ -15,6 +15,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -47,6 +48,7 @@ struct ndtpso_ctx {
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
+  int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the most recent upload / results call
   int sm_count = 0;
   int max_smem_optin = 0;
   std::vector<PoolBuf> dev_pool, pin_pool;
@@ -169,9 +171,84 @@ int validate_problem(ndtpso_ctx* ctx, const ndtpso_problem& p, int b) {
   return NDTPSO_OK;
 }
 
-// Builds the arena for `n` problems; conf == nullptr => cost-only batch (no rand streams).
-int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, size_t extra_upload_bytes,
-                size_t extra_device_bytes, ndtpso_batch** out, size_t* extra_upload_off, size_t* extra_device_off) {
+// Runs f(i) for i in [0, n) on up to `max_threads` host threads (staging is memcpy/scan bound).
+template <class F>
+void parallel_for(int n, int max_threads, F f) {
+  int nt = std::min<int>(max_threads, (int)std::thread::hardware_concurrency());
+  nt = std::min(nt, n / 8);  // not worth a thread for fewer than 8 items
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=]() {
+      for (int i = t; i < n; i += nt) f(i);
+    });
+  for (auto& x : th) x.join();
+}
+
+// What the host learns from one pass over a table: which cells are built, the grid rows they
+// span (=> shared-memory need of the compact form), and whether Sigma^-1 is symmetric.
+struct MapScan {
+  std::vector<int> cells;  // built cell indices, ascending (dense input); empty for sparse input
+  int n_rec = 0, row0 = 0, nrows = 0;
+  bool symmetric = true, ok = true;
+};
+
+void scan_map(const ndtpso_map_view& m, bool want_cells, MapScan* out) {
+  const int ncells = m.w_cells * m.h_cells;
+  int ay = INT_MAX, by = -1, n_rec = 0;
+  auto note = [&](int cell, size_t row) {
+    const int iy = cell / m.w_cells;
+    ay = std::min(ay, iy);
+    by = std::max(by, iy);
+    ++n_rec;
+    if (memcmp(&m.inv_cov[4 * row + 1], &m.inv_cov[4 * row + 2], sizeof(double)) != 0) out->symmetric = false;
+  };
+  if (m.n_sparse >= 0) {
+    for (int r = 0; r < m.n_sparse; ++r) {
+      const int cell = m.cell_index[r];
+      if (cell < 0 || cell >= ncells || (r > 0 && cell <= m.cell_index[r - 1])) {
+        out->ok = false;
+        return;
+      }
+      note(cell, (size_t)r);
+    }
+  } else {
+    if (want_cells) out->cells.reserve(1024);
+    int c = 0;
+    for (; c + 8 <= ncells; c += 8) {  // tables are sparse: test 8 flags at a time
+      uint64_t w;
+      memcpy(&w, m.built + c, 8);
+      if (!w) continue;
+      for (int k = 0; k < 8; ++k)
+        if (m.built[c + k]) {
+          note(c + k, (size_t)(c + k));
+          if (want_cells) out->cells.push_back(c + k);
+        }
+    }
+    for (; c < ncells; ++c)
+      if (m.built[c]) {
+        note(c, (size_t)c);
+        if (want_cells) out->cells.push_back(c);
+      }
+  }
+  out->n_rec = n_rec;
+  out->row0 = n_rec ? ay : 0;
+  out->nrows = n_rec ? by - ay + 1 : 0;
+}
+
+// Builds the arena for `n` problems and fills the pinned staging copy.
+//   conf == nullptr     cost-only batch (no rand streams)
+//   compact_on_host     dense tables are staged in the sparse form (built cells only): the host
+//                       scans the `built` flags anyway, and the H2D copy shrinks from 49 bytes per
+//                       cell to 52 bytes per BUILT cell.  Used by the host-buffer entry points;
+//                       ndtpso_batch_create keeps dense tables dense (K0 compacts them on the device).
+int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, bool compact_on_host,
+                size_t extra_upload_bytes, size_t extra_device_bytes, ndtpso_batch** out, size_t* extra_upload_off,
+                size_t* extra_device_off) {
   if (!ctx || !out || n < 0 || (n > 0 && !problems)) return fail(ctx, NDTPSO_ERR_ARG, "batch: null argument or negative count");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   PsoParams prm{};
@@ -211,6 +288,13 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     map_of[b] = it->second;
   }
   const int M = (int)maps.size();
+  constexpr int kHostThreads = 8;
+
+  // ---- one pass over every table
+  std::vector<MapScan> scans(M);
+  parallel_for(M, kHostThreads, [&](int i) { scan_map(*maps[i], compact_on_host, &scans[i]); });
+  for (int i = 0; i < M; ++i)
+    if (!scans[i].ok) return fail(ctx, NDTPSO_ERR_ARG, "sparse map: cell_index must be strictly ascending and inside the grid");
 
   // ---- arena layout
   size_t off = 0;
@@ -225,14 +309,16 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   for (int b = 0; b < n; ++b) o_pts[b] = take((size_t)problems[b].n_points * 16);
   std::vector<size_t> o_mean(M), o_icov(M), o_built(M), o_cidx(M);
   std::vector<int> rows(M);
+  std::vector<char> staged_sparse(M);
   for (int i = 0; i < M; ++i) {
     const ndtpso_map_view& m = *maps[i];
     const int ncells = m.w_cells * m.h_cells;
-    rows[i] = m.n_sparse >= 0 ? m.n_sparse : ncells;
+    staged_sparse[i] = (m.n_sparse >= 0) || (compact_on_host && scans[i].n_rec <= 65534);
+    rows[i] = m.n_sparse >= 0 ? m.n_sparse : (staged_sparse[i] ? scans[i].n_rec : ncells);
     o_mean[i] = take((size_t)rows[i] * 16);
     o_icov[i] = take((size_t)rows[i] * 32);
-    o_built[i] = m.n_sparse >= 0 ? 0 : take((size_t)ncells);
-    o_cidx[i] = m.n_sparse >= 0 ? take((size_t)rows[i] * 4) : 0;
+    o_built[i] = staged_sparse[i] ? 0 : take((size_t)ncells);
+    o_cidx[i] = staged_sparse[i] ? take((size_t)rows[i] * 4) : 0;
   }
   bool any_device_rng = false;
   if (conf)
@@ -250,8 +336,8 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   for (int i = 0; i < M; ++i) {
     const ndtpso_map_view& m = *maps[i];
     o_hdr[i] = take(sizeof(int) * HDR_WORDS);
-    o_grid[i] = take(((size_t)m.w_cells * m.h_cells + 1) * 2 + 16);  // row strip (<= all rows) + null slot
-    o_rec[i] = take(((size_t)rows[i] + 1) * 48);                      // records + null record
+    o_grid[i] = take(((size_t)scans[i].nrows * m.w_cells + 1) * 2 + 16);  // row strip + null slot
+    o_rec[i] = take(((size_t)scans[i].n_rec + 1) * 48);                   // records + null record
   }
   if (conf)
     for (int b = 0; b < n; ++b)
@@ -281,11 +367,12 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   bt->d_out = reinterpret_cast<double*>(d + o_out);
   bt->d_stats = reinterpret_cast<int*>(d + o_stats);
 
-  // ---- fill the staging buffer
+  // ---- fill the staging buffer (tables and scans in parallel: pure memcpy / gather)
   DevMap* hm = reinterpret_cast<DevMap*>(h + o_maps);
   std::vector<int> map_dyn(M, 0);
-  for (int i = 0; i < M; ++i) {
+  parallel_for(M, kHostThreads, [&](int i) {
     const ndtpso_map_view& m = *maps[i];
+    const MapScan& sc = scans[i];
     const int ncells = m.w_cells * m.h_cells;
     DevMap dm{};
     dm.x_min = m.x_min;
@@ -300,54 +387,45 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     dm.gw = m.w_cells;
     dm.gh = m.h_cells;
     dm.ncells = ncells;
-    dm.n_sparse = m.n_sparse;
+    dm.n_sparse = staged_sparse[i] ? rows[i] : -1;
     dm.mean = reinterpret_cast<const double*>(d + o_mean[i]);
     dm.icov = reinterpret_cast<const double*>(d + o_icov[i]);
-    dm.built = m.n_sparse >= 0 ? nullptr : d + o_built[i];
-    dm.cell_index = m.n_sparse >= 0 ? reinterpret_cast<const int*>(d + o_cidx[i]) : nullptr;
+    dm.built = staged_sparse[i] ? nullptr : d + o_built[i];
+    dm.cell_index = staged_sparse[i] ? reinterpret_cast<const int*>(d + o_cidx[i]) : nullptr;
     dm.grid = reinterpret_cast<unsigned short*>(d + o_grid[i]);
     dm.rec = reinterpret_cast<double*>(d + o_rec[i]);
     dm.hdr = reinterpret_cast<int*>(d + o_hdr[i]);
     hm[i] = dm;
-    if (rows[i]) {
-      memcpy(h + o_mean[i], m.mean, (size_t)rows[i] * 16);
-      memcpy(h + o_icov[i], m.inv_cov, (size_t)rows[i] * 32);
-    }
-    // shared-memory need of this table (built cells and the grid rows they span), known on the host for free
-    int n_rec = 0, ay = INT_MAX, by = -1;
-    auto note = [&](int cell) {
-      const int iy = cell / m.w_cells;
-      ay = std::min(ay, iy);
-      by = std::max(by, iy);
-      ++n_rec;
-    };
-    if (m.n_sparse >= 0) {
-      if (rows[i]) memcpy(h + o_cidx[i], m.cell_index, (size_t)rows[i] * 4);
-      for (int r = 0; r < rows[i]; ++r) {
-        const int cell = m.cell_index[r];
-        if (cell < 0 || cell >= ncells || (r > 0 && cell <= m.cell_index[r - 1])) {
-          ndtpso_batch_destroy(bt);
-          return fail(ctx, NDTPSO_ERR_ARG, "sparse map: cell_index must be strictly ascending and inside the grid");
-        }
-        note(cell);
-        if (memcmp(&m.inv_cov[4 * (size_t)r + 1], &m.inv_cov[4 * (size_t)r + 2], sizeof(double)) != 0) bt->all_symmetric = false;
+    if (m.n_sparse >= 0 || !staged_sparse[i]) {  // as given
+      if (rows[i]) {
+        memcpy(h + o_mean[i], m.mean, (size_t)rows[i] * 16);
+        memcpy(h + o_icov[i], m.inv_cov, (size_t)rows[i] * 32);
       }
-    } else {
-      memcpy(h + o_built[i], m.built, (size_t)ncells);
-      for (int c = 0; c < ncells; ++c)
-        if (m.built[c]) {
-          note(c);
-          if (memcmp(&m.inv_cov[4 * (size_t)c + 1], &m.inv_cov[4 * (size_t)c + 2], sizeof(double)) != 0) bt->all_symmetric = false;
-        }
+      if (m.n_sparse >= 0) {
+        if (rows[i]) memcpy(h + o_cidx[i], m.cell_index, (size_t)rows[i] * 4);
+      } else {
+        memcpy(h + o_built[i], m.built, (size_t)ncells);
+      }
+    } else {  // dense -> sparse on the host
+      double* hmean = reinterpret_cast<double*>(h + o_mean[i]);
+      double* hicov = reinterpret_cast<double*>(h + o_icov[i]);
+      int* hcidx = reinterpret_cast<int*>(h + o_cidx[i]);
+      for (int r = 0; r < sc.n_rec; ++r) {
+        const size_t c = (size_t)sc.cells[r];
+        hcidx[r] = (int)c;
+        memcpy(hmean + 2 * (size_t)r, m.mean + 2 * c, 16);
+        memcpy(hicov + 4 * (size_t)r, m.inv_cov + 4 * c, 32);
+      }
     }
-    const int nrows = n_rec ? by - ay + 1 : 0;
-    map_dyn[i] = (n_rec + 1) * 48 + round16((nrows * m.w_cells + 1) * 2);
+    map_dyn[i] = (sc.n_rec + 1) * 48 + round16((sc.nrows * m.w_cells + 1) * 2);
+  });
+  for (int i = 0; i < M; ++i) {
     bt->max_table_smem = std::max(bt->max_table_smem, map_dyn[i]);
-    if (n_rec > 65534) bt->all_compact = false;
+    if (scans[i].n_rec > 65534) bt->all_compact = false;
+    if (!scans[i].symmetric) bt->all_symmetric = false;
   }
   DevProblem* hp = reinterpret_cast<DevProblem*>(h + o_probs);
-  int need = 0;
-  for (int b = 0; b < n; ++b) {
+  parallel_for(n, kHostThreads, [&](int b) {
     const ndtpso_problem& p = problems[b];
     DevProblem dp{};
     dp.pts = reinterpret_cast<const double2*>(d + o_pts[b]);
@@ -363,8 +441,11 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     hp[b] = dp;
     if (p.n_points) memcpy(h + o_pts[b], p.points_xy, (size_t)p.n_points * 16);
     if (conf && p.rand_stream) memcpy(h + o_rnd[b], p.rand_stream, (size_t)prm.n_draws * 4);
-    need = std::max(need, p.n_points * 16 + map_dyn[map_of[b]]);
-    bt->max_pts = std::max(bt->max_pts, p.n_points);
+  });
+  int need = 0;
+  for (int b = 0; b < n; ++b) {
+    need = std::max(need, problems[b].n_points * 16 + map_dyn[map_of[b]]);
+    bt->max_pts = std::max(bt->max_pts, problems[b].n_points);
   }
   bt->need_dyn_smem = need;
   if (extra_upload_off) *extra_upload_off = o_extra_up;
@@ -376,6 +457,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
 int batch_upload(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   CUDA_TRY(ctx, cudaMemcpyAsync(bt->dev.ptr, bt->pin.ptr, bt->upload_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->last_h2d = (int64_t)bt->upload_bytes;
   return NDTPSO_OK;
 }
 
@@ -589,17 +671,25 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
 
 int64_t ndtpso_ctx_launch_count(const ndtpso_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int ndtpso_ctx_last_transfer_bytes(const ndtpso_ctx* ctx, int64_t* h2d, int64_t* d2h) {
+  if (!ctx) return NDTPSO_ERR_ARG;
+  if (h2d) *h2d = ctx->last_h2d;
+  if (d2h) *d2h = ctx->last_d2h;
+  return NDTPSO_OK;
+}
+
 int ndtpso_ctx_synchronize(ndtpso_ctx* ctx) {
   if (!ctx) return NDTPSO_ERR_ARG;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NDTPSO_OK;
 }
 
-int ndtpso_batch_create(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out) {
+static int batch_create_impl(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, bool compact_on_host,
+                             ndtpso_batch** out) {
   if (!conf) return fail(ctx, NDTPSO_ERR_ARG, "batch_create: null config");
   if (out) *out = nullptr;
   ndtpso_batch* bt = nullptr;
-  int rc = batch_build(ctx, n, problems, conf, 0, 0, &bt, nullptr, nullptr);
+  int rc = batch_build(ctx, n, problems, conf, compact_on_host, 0, 0, &bt, nullptr, nullptr);
   if (rc) return rc;
   rc = batch_upload(bt);
   if (rc) {
@@ -608,6 +698,11 @@ int ndtpso_batch_create(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* proble
   }
   *out = bt;
   return NDTPSO_OK;
+}
+
+int ndtpso_batch_create(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out) {
+  // tables stay in the form the caller gave: dense ones are compacted by K0 on the device at every solve
+  return batch_create_impl(ctx, n, problems, conf, false, out);
 }
 
 int ndtpso_batch_solve(ndtpso_batch* bt) {
@@ -672,6 +767,7 @@ int ndtpso_batch_results(ndtpso_batch* bt, double* out_pose, double* out_cost) {
   double* h = static_cast<double*>(bt->pin.ptr);
   CUDA_TRY(ctx, cudaMemcpyAsync(h, bt->d_out, sizeof(double) * 4 * (size_t)bt->n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->last_d2h = (int64_t)sizeof(double) * 4 * bt->n;
   for (int b = 0; b < bt->n; ++b) {
     if (out_pose) {
       out_pose[3 * b] = h[4 * b];
@@ -710,7 +806,7 @@ int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problem
                        double* out_cost) {
   if (!ctx || !conf || (n > 0 && !out_pose)) return fail(ctx, NDTPSO_ERR_ARG, "align_batch: null argument");
   ndtpso_batch* bt = nullptr;
-  int rc = ndtpso_batch_create(ctx, n, problems, conf, &bt);
+  int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // built cells only cross PCIe
   if (rc) return rc;
   rc = ndtpso_batch_solve(bt);
   if (rc == NDTPSO_OK) rc = ndtpso_batch_results(bt, out_pose, out_cost);
@@ -725,7 +821,7 @@ int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems
   const size_t cost_bytes = sizeof(double) * (size_t)n * n_poses;
   ndtpso_batch* bt = nullptr;
   size_t o_up = 0, o_dev = 0;
-  int rc = batch_build(ctx, n, problems, nullptr, pose_bytes, cost_bytes, &bt, &o_up, &o_dev);
+  int rc = batch_build(ctx, n, problems, nullptr, true, pose_bytes, cost_bytes, &bt, &o_up, &o_dev);
   if (rc) return rc;
   auto cleanup = [&](int code) {
     ndtpso_batch_destroy(bt);

@@ -74,13 +74,20 @@ class NoiseLCG:
         self.state = state & 0xFFFFFFFF
 
     def uniform(self, n: int) -> np.ndarray:
-        out = np.empty(n, dtype=np.float64)
-        s = self.state
-        for i in range(n):
-            s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
-            out[i] = (s >> 8) / 16777216.0
-        self.state = s
-        return out
+        """The next n draws.  s_k = a^k s_0 + c (1 + a + ... + a^(k-1)) mod 2^32, evaluated with wrapping
+        uint32 accumulations (bit-identical to stepping the recurrence n times)."""
+        if n <= 0:
+            return np.empty(0, dtype=np.float64)
+        u32 = np.uint32
+        a_pow = np.multiply.accumulate(np.full(n, 1664525, dtype=u32), dtype=u32)  # a^1 .. a^n (wrapping)
+        ones = np.empty(n, dtype=u32)
+        ones[0] = 1
+        ones[1:] = a_pow[:-1]
+        geo = np.add.accumulate(ones, dtype=u32)  # 1 + a + .. + a^(k-1)
+        with np.errstate(over="ignore"):
+            s = a_pow * u32(self.state) + u32(1013904223) * geo
+        self.state = int(s[-1])
+        return (s >> np.uint32(8)).astype(np.float64) / 16777216.0
 
 
 class Room:

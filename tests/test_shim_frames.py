@@ -1,0 +1,145 @@
+"""The drop-in NDTFrame (host map building, ndtpso_slam_b200/shim) against the reference.
+
+CPU tests: the (mean, inverse covariance, built) tables and scan points it builds from the synthetic
+scans are bit-identical to the reference's (golden fixtures; and the live reference where present).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from ndtpso_slam_b200 import frames, synthetic as syn
+
+CASES = [("cfg1", syn.CFG1), ("cfg2", syn.CFG2), ("cfg5_0.25", syn.CFG5[0.25]), ("cfg5_2.0", syn.CFG5[2.0]),
+         ("np2", syn.MatchConfig("np2", syn.SENSOR_361, 20, 0.3, 20, 15))]
+
+
+def test_exports_every_declared_symbol():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "ndtpso_frames.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ndtpso_frame_[a-z0-9_]+)\s*\(", src)))
+    lib = frames.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(frames.EXPORTS) == declared
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+def test_tables_match_golden_bit_for_bit(golden, name, cfg):
+    want = golden.flat(name)
+    got = frames.problem_from_scans(syn.scene_a(cfg))
+    for k in ("w_cells", "h_cells", "width_m", "height_m", "cell_side", "x_min", "x_max", "y_min", "y_max"):
+        assert got[k] == want[k], k
+    assert np.array_equal(got["points"], want["points"])
+    assert np.array_equal(got["built"], want["built"])
+    b = want["built"].astype(bool)
+    assert np.array_equal(got["mean"][b], want["mean"][b])
+    assert np.array_equal(got["inv_cov"][b], want["inv_cov"][b])
+    sp = frames.problem_from_scans(syn.scene_a(cfg), sparse=True)
+    assert np.array_equal(sp["cell_index"], np.nonzero(b)[0])
+    assert np.array_equal(sp["mean"], want["mean"][b]) and np.array_equal(sp["inv_cov"], want["inv_cov"][b])
+
+
+def test_trajectory_problem_matches_golden(golden):
+    want = golden.flat("traj17")
+    got = frames.problem_from_scans(syn.trajectory_problem(syn.CFG2, 17))
+    assert np.array_equal(got["points"], want["points"]) and np.array_equal(got["built"], want["built"])
+    b = want["built"].astype(bool)
+    assert np.array_equal(got["inv_cov"][b], want["inv_cov"][b])
+
+
+def test_sliding_window_against_live_reference(reference):
+    """Many scans into one map: cells overflow their 50-point slots and the window advances
+    (ndtcell.cpp:61-65); repeated build() calls re-add the slot statistics (ndtcell.cpp:37-55)."""
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    room, noise = syn.Room(S), syn.NoiseLCG(99)
+    mine = frames.Frame(width=S, height=S, cell_side=cfg.cell_side)
+    ref = reference.frame(width=S, height=S, cell_side=cfg.cell_side, init_windows=True)
+    for k in range(40):
+        pose = (0.03 * k, 0.01 * k, 0.004 * k)
+        ranges = syn.make_scan(room, s, pose, noise)
+        a = frames.Frame(width=S, height=S, cell_side=float(S), calculate_cells_params=False)
+        b = reference.frame(width=S, height=S, cell_side=float(S), init_windows=False)
+        a.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+        b.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+        assert np.array_equal(a.scan_points(), b.flatten_points())
+        mine.update(pose, a)
+        ref.update(pose, b)
+        if k % 3 == 2:  # the node rebuilds lazily before every match
+            mine.build()
+            ref.build()
+            got, want = mine.map_table(), ref.flatten_map()
+            assert np.array_equal(got["built"], want["built"]), k
+            m = want["built"].astype(bool)
+            assert np.array_equal(got["mean"][m], want["mean"][m]), k
+            assert np.array_equal(got["inv_cov"][m], want["inv_cov"][m]), k
+    assert mine.point_count() == reference.lib.ref_frame_count_all_points(ref.h)
+    assert mine.point_count() > 40 * 300
+
+
+def test_initial_pose_pretransform(reference):
+    """A frame constructed with a non-zero `trans` pre-transforms every beam (ndtframe.cpp:152,175)."""
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    ranges = syn.make_scan(syn.Room(S), s, (0.1, 0.2, 0.3), syn.NoiseLCG(5))
+    a = frames.Frame(trans=(0.5, -0.25, 0.125), width=S, height=S, cell_side=float(S), calculate_cells_params=False)
+    b = reference.frame(trans=(0.5, -0.25, 0.125), width=S, height=S, cell_side=float(S), init_windows=False)
+    a.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+    b.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+    assert np.array_equal(a.scan_points(), b.flatten_points())
+
+
+def test_dump_map_csv(tmp_path):
+    """dumpMap writes the reference's CSV/gnuplot trio (ndtframe.cpp:268-391)."""
+    ref, q = frames.frames_from_scans(syn.scene_a(syn.CFG1))
+    ref.add_pose(1.5, (0.1, 0.2, 0.3))
+    ref.add_pose(2.5, (0.4, 0.5, 0.6))
+    base = str(tmp_path / "map")
+    ref.dump_map(base)
+    pts = open(base + ".map.csv").read().splitlines()
+    assert pts[0] == "x,y" and len(pts) == 1 + ref.point_count() == 1 + 5 * 361
+    poses = open(base + ".pose.csv").read().splitlines()
+    assert poses[0] == "timestamp,xP,yP,thP,xO,yO,thO"
+    assert poses[1] == "1.500000,0.10000,0.20000,0.30000" and len(poses) == 3
+    assert "plot '" in open(base + ".gnuplot").read()
+
+
+@pytest.mark.gpu
+def test_align_chain_matches_reference(golden):
+    """Four chained NDTFrame::align calls on the process-global rand() stream after srand(7): the
+    deviation rule, s_* bookkeeping and the host-drawn random stream reproduce the reference's poses."""
+    libc = C.CDLL(None)
+    libc.srand(int(golden.z["align_chain/srand"][0]))
+    ref, q = frames.frames_from_scans(syn.scene_a(syn.CFG_ALIGN_DEFAULT))
+    want = golden.z["align_chain/pose"]
+    guess = np.array(syn.DEFAULT_GUESS)
+    for k in range(len(want)):
+        pose = ref.align(guess, q)
+        assert np.abs(pose - want[k]).max() <= 1e-4, (k, pose, want[k])
+        guess = pose
+
+
+@pytest.mark.gpu
+def test_cost_function_through_frames(golden):
+    ref, q = frames.frames_from_scans(syn.scene_a(syn.CFG1))
+    poses, want = golden.z["cfg1/cost_poses"], golden.z["cfg1/cost_values"]
+    for p, w in list(zip(poses, want))[:12]:
+        got = ref.cost(q, p)
+        assert abs(got - w) <= 1e-9 * max(abs(w), 1e-300)
+
+
+@pytest.mark.gpu
+def test_align_with_explicit_config(golden, oracle):
+    """align(guess, frame, PSOConfig): the overload that honours the node's PSO parameters."""
+    from ndtpso_slam_b200 import capi
+    libc = C.CDLL(None)
+    libc.srand(3)
+    ss = syn.scene_a(syn.CFG1)
+    ref, q = frames.frames_from_scans(ss)
+    pose = ref.align(ss.guess, q, capi.PsoConfig.make(population=30, iterations=20))
+    c = golden.case("cfg1")
+    i = c["seeds"].index(3)
+    assert np.abs(pose - c["pose"][i]).max() <= 1e-4

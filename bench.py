@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -195,7 +195,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from ndtpso_slam_b200 import capi
+    from ndtpso_slam_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,7 +229,6 @@ def run_gpu_arm(args):
     d2h_bytes = B * 32
 
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    gathered = torch.empty(world * B * 4, dtype=torch.float64, device="cuda") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -248,8 +247,8 @@ def run_gpu_arm(args):
 
     def resident_step():
         bt.solve()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, res_t)
+        if world > 1:  # the one exchange of the path: every rank gets all solved poses
+            sharding.gather_results(res_t.view(B, 4), world * B, world, rank)
 
     for _ in range(args.warmup):
         l2_flush.fill_(1)
@@ -336,7 +335,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="scan-match problems per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -490,21 +490,34 @@ int launch_pso(ndtpso_batch* bt, int smem) {
 }
 
 // Point-sliced kernel: T = 32*NW threads hold NPT scan points each and score JB candidates at a
-// time.  launch_sliced returns 1 when the batch does not qualify (table too large for shared
-// memory, scan too long, > 65534 built cells).
-template <int NPT, int JB, int MAXT, int MINB>
-int launch_sliced_cfg(ndtpso_batch* bt, int nw, int smem) {
+// time; a problem may be spread over a cluster of CL CTAs (G candidate groups x S point slices).
+// launch_sliced returns 1 when the batch does not qualify (table too large for shared memory,
+// scan too long, > 65534 built cells, asymmetric Sigma^-1).
+template <int NPT, int JB, int CL, int MAXT, int MINB>
+int launch_sliced_cfg(ndtpso_batch* bt, int nw, int groups, int smem) {
   ndtpso_ctx* ctx = bt->ctx;
+  auto kern = pso_sliced_kernel<NPT, JB, CL, MAXT, MINB>;
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(pso_sliced_kernel<NPT, JB, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ctx->max_smem_optin));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    if (CL > 8) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set[ctx->device & 63] = true;
   }
   PsoParams prm = bt->prm;
   prm.smem_bytes = smem;
-  pso_sliced_kernel<NPT, JB, MAXT, MINB><<<bt->n, nw * 32, smem, ctx->stream>>>(bt->d_probs, bt->d_maps, prm, bt->d_out, bt->d_stats);
-  CUDA_TRY(ctx, cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)bt->n * CL, 1, 1);
+  cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, (const DevProblem*)bt->d_probs, (const DevMap*)bt->d_maps, prm, groups, bt->d_out, bt->d_stats));
   ctx->launches++;
   return NDTPSO_OK;
 }
@@ -512,10 +525,76 @@ int launch_sliced_cfg(ndtpso_batch* bt, int nw, int smem) {
 // maximum warps per CTA of each points-per-thread variant (its __launch_bounds__)
 constexpr int kSlicedMaxWarps[kSlicedMaxNPT + 1] = {0, 20, 20, 12, 10, 8, 8};
 
+// Cluster form of the sliced kernel for one cluster size: S = min(CL, 4) point slices, G = CL / S
+// candidate groups, 4 candidates per batch.  Returns 1 when the shape does not fit (scan too long
+// for 12 warps x 2 points per thread, table too large) or when fewer than n clusters of this size
+// can be resident at once (cudaOccupancyMaxActiveClusters; e.g. only ~14 clusters of 8 fit the
+// GPCs of a B200, so 16 problems are faster on clusters of 4) unless the size was forced.
+template <int CL>
+int try_cluster(ndtpso_batch* bt, bool forced) {
+  ndtpso_ctx* ctx = bt->ctx;
+  const int n = std::max(bt->max_pts, 1);
+  const int S = std::min(CL, 4), G = CL / S;
+  int npt = 1, nw = (n + 32 * S - 1) / (32 * S);
+  if (nw > 12) {
+    npt = 2;
+    nw = (n + 64 * S - 1) / (64 * S);
+  }
+  if (nw > 12) return 1;
+  nw = std::max(nw, 2);
+  const int smem = round16(sliced_smem_bytes(bt->prm.P, S, nw, bt->max_table_smem));
+  if (smem > ctx->max_smem_optin) return 1;
+  if (!forced) {
+    const void* kern = npt == 1 ? (const void*)pso_sliced_kernel<1, 8, CL, 384, 1> : (const void*)pso_sliced_kernel<2, 4, CL, 384, 1>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin) != cudaSuccess ||
+        (CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+      cudaGetLastError();
+      return 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)bt->n * CL, 1, 1);
+    cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return 1;
+    }
+    if (bt->n > max_clusters) return 1;
+  }
+  return npt == 1 ? launch_sliced_cfg<1, 8, CL, 384, 1>(bt, nw, G, smem) : launch_sliced_cfg<2, 4, CL, 384, 1>(bt, nw, G, smem);
+}
+
 int launch_sliced(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   if (!bt->all_compact || !bt->all_symmetric) return 1;
   const int n = std::max(bt->max_pts, 1);
+  // Spread a problem over a cluster of SMs only while the batch alone leaves SMs idle: the
+  // largest cluster size whose clusters can all be resident together.
+  if (ctx->opt_cluster > 1) {
+    int rc = 1;
+    switch (ctx->opt_cluster) {
+      case 2: rc = try_cluster<2>(bt, true); break;
+      case 4: rc = try_cluster<4>(bt, true); break;
+      case 8: rc = try_cluster<8>(bt, true); break;
+      default: rc = try_cluster<16>(bt, true); break;
+    }
+    if (rc != 1) return rc;
+  } else if (ctx->opt_cluster == 0 && bt->n * 2 <= ctx->sm_count) {
+    int rc = 1;
+    if (bt->n * 16 <= ctx->sm_count) rc = try_cluster<16>(bt, false);
+    if (rc == 1 && bt->n * 8 <= ctx->sm_count) rc = try_cluster<8>(bt, false);
+    if (rc == 1 && bt->n * 4 <= ctx->sm_count) rc = try_cluster<4>(bt, false);
+    if (rc == 1) rc = try_cluster<2>(bt, false);
+    if (rc != 1) return rc;
+  }
   int npt = 0, nw = 0;
   if (ctx->opt_npt > 0) {
     npt = std::min(ctx->opt_npt, kSlicedMaxNPT);
@@ -535,18 +614,18 @@ int launch_sliced(ndtpso_batch* bt) {
   }
   if (npt < 1 || npt > kSlicedMaxNPT || nw > kSlicedMaxWarps[npt]) return 1;
   nw = std::max(nw, 4);
-  const int smem = round16(sliced_smem_bytes(bt->prm.P, nw, bt->max_table_smem));
+  const int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem));
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;
   switch (npt) {
-    case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 640, 1>(bt, nw, smem) : jb == 2 ? launch_sliced_cfg<1, 2, 640, 1>(bt, nw, smem)
-                                                                                     : launch_sliced_cfg<1, 4, 640, 1>(bt, nw, smem);
-    case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 640, 1>(bt, nw, smem) : jb == 2 ? launch_sliced_cfg<2, 2, 640, 1>(bt, nw, smem)
-                                                                                     : launch_sliced_cfg<2, 4, 640, 1>(bt, nw, smem);
-    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 384, 2>(bt, nw, smem) : launch_sliced_cfg<3, 2, 384, 2>(bt, nw, smem);
-    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 320, 2>(bt, nw, smem) : launch_sliced_cfg<4, 2, 320, 2>(bt, nw, smem);
-    case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 256, 2>(bt, nw, smem) : launch_sliced_cfg<5, 2, 256, 2>(bt, nw, smem);
-    default: return jb == 1 ? launch_sliced_cfg<6, 1, 256, 2>(bt, nw, smem) : launch_sliced_cfg<6, 2, 256, 2>(bt, nw, smem);
+    case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 1, 640, 1>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<1, 2, 1, 640, 1>(bt, nw, 1, smem)
+                                                                                        : launch_sliced_cfg<1, 4, 1, 640, 1>(bt, nw, 1, smem);
+    case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 1, 640, 1>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<2, 2, 1, 640, 1>(bt, nw, 1, smem)
+                                                                                        : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem);
+    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem) : launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem);
+    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem);
+    case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem);
+    default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem);
   }
 }
 
@@ -661,7 +740,8 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
       ctx->opt_smem = value;
       return NDTPSO_OK;
     case NDTPSO_OPT_CLUSTER:
-      if (value < 0 || value > 1) return fail(ctx, NDTPSO_ERR_ARG, "cluster size not supported");
+      if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+        return fail(ctx, NDTPSO_ERR_ARG, "cluster size must be 0 (auto), 1, 2, 4, 8 or 16");
       ctx->opt_cluster = (int)value;
       return NDTPSO_OK;
     default:

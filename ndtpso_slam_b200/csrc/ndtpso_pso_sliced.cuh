@@ -31,6 +31,22 @@ enum {
 };
 constexpr int kProdVariant = 0;
 
+// Phase timing (tools/score_bench.cu builds with -DNDTPSO_PHASE_TIMING): thread 0 of every CTA adds the
+// cycles it spends in {prologue+init, phase A, phase B, phase C} (barrier waits included) to g_phase_cycles.
+#ifdef NDTPSO_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define NDTPSO_PHASE_DECL long long ph_t0 = clock64();
+#define NDTPSO_PHASE_MARK(i)                                                         \
+  if (threadIdx.x == 0) {                                                            \
+    const long long ph_t1 = clock64();                                               \
+    atomicAdd(&g_phase_cycles[i], static_cast<unsigned long long>(ph_t1 - ph_t0));   \
+    ph_t0 = ph_t1;                                                                   \
+  }
+#else
+#define NDTPSO_PHASE_DECL
+#define NDTPSO_PHASE_MARK(i)
+#endif
+
 struct __align__(16) Pose {
   double x, y, c, s, th, pad;  // {x, y} and {cos, sin} are the two 16-byte loads of phase B
 };
@@ -45,7 +61,8 @@ struct SlicedSmem {
   double* cst;      // [8] fast_exp constants
   unsigned char* table;  // records, then grid
   Pose* pose;       // [2][P+1]
-  double* partial;  // [2][(P+1)*NW]
+  double* partial;  // [2][(P+1)*PW]
+  double* wpart;    // [(P+1)*NW] warp partials of the cluster form (unused when CL == 1)
   double* cost0;    // [P+1] initial costs
   double* x;        // [P][3]  owner-private particle state
   double* v;        // [P][3]
@@ -54,20 +71,22 @@ struct SlicedSmem {
   double* pbc;      // [P]
 };
 
-__host__ __device__ inline int sliced_swarm_smem_bytes(int P, int NW) {
+// PW = partials per candidate summed in phase C; WP = warp partials per candidate of the cluster form (0 when CL == 1)
+__host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   const int Pn = P > 0 ? P : 1;
   int b = 2 * (P + 1) * (int)sizeof(Pose);
-  b += 2 * (P + 1) * NW * (int)sizeof(double);
+  b += 2 * (P + 1) * PW * (int)sizeof(double);
+  b += (P + 1) * WP * (int)sizeof(double);
   b += (P + 1) * (int)sizeof(double);
   b += Pn * 13 * (int)sizeof(double);
   return (b + 15) & ~15;
 }
 // total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2)
-__host__ __device__ inline int sliced_smem_bytes(int P, int NW, int table_bytes) {
-  return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, NW);
+__host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int table_bytes) {
+  return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP);
 }
 
-__device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int NW, int table_bytes) {
+__device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int PW, int WP, int table_bytes) {
   SlicedSmem s;
   const int Pn = P > 0 ? P : 1;
   s.bar = reinterpret_cast<uint64_t*>(base);
@@ -78,7 +97,9 @@ __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, i
   s.pose = reinterpret_cast<Pose*>(p);
   p += 2 * (P + 1) * sizeof(Pose);
   s.partial = reinterpret_cast<double*>(p);
-  p += 2 * (size_t)(P + 1) * NW * sizeof(double);
+  p += 2 * (size_t)(P + 1) * PW * sizeof(double);
+  s.wpart = reinterpret_cast<double*>(p);
+  p += (size_t)(P + 1) * WP * sizeof(double);
   s.cost0 = reinterpret_cast<double*>(p);
   p += (P + 1) * sizeof(double);
   double* d = reinterpret_cast<double*>(p);
@@ -218,23 +239,75 @@ __device__ __forceinline__ double packed_warp_sum<4>(const double (&a)[4], int l
   for (int off = 4; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
   return k;
 }
+template <>
+__device__ __forceinline__ double packed_warp_sum<8>(const double (&a)[8], int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0, hi4 = (lane & 4) != 0;
+  double k01 = hi16 ? a[1] : a[0];
+  k01 += __shfl_xor_sync(0xffffffffu, hi16 ? a[0] : a[1], 16);
+  double k23 = hi16 ? a[3] : a[2];
+  k23 += __shfl_xor_sync(0xffffffffu, hi16 ? a[2] : a[3], 16);
+  double k45 = hi16 ? a[5] : a[4];
+  k45 += __shfl_xor_sync(0xffffffffu, hi16 ? a[4] : a[5], 16);
+  double k67 = hi16 ? a[7] : a[6];
+  k67 += __shfl_xor_sync(0xffffffffu, hi16 ? a[6] : a[7], 16);
+  double ka = hi8 ? k23 : k01;
+  ka += __shfl_xor_sync(0xffffffffu, hi8 ? k01 : k23, 8);
+  double kb = hi8 ? k67 : k45;
+  kb += __shfl_xor_sync(0xffffffffu, hi8 ? k45 : k67, 8);
+  double k = hi4 ? kb : ka;
+  k += __shfl_xor_sync(0xffffffffu, hi4 ? ka : kb, 4);  // bit 2 clear: candidates 0..3; set: 4..7
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
 template <int JB>
 __device__ __forceinline__ int packed_slot(int lane) {
   if (JB == 1) return 0;
   if (JB == 2) return (lane >> 4) & 1;
-  return ((lane >> 4) & 1) + ((lane >> 3) & 1) * 2;
+  if (JB == 4) return ((lane >> 4) & 1) + ((lane >> 3) & 1) * 2;
+  return ((lane >> 4) & 1) + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) * 4;
 }
 template <int JB>
 __device__ __forceinline__ bool packed_writer(int lane) {
-  return JB == 4 ? (lane & 7) == 0 : JB == 2 ? (lane & 15) == 0 : lane == 0;
+  return (lane & (32 / JB - 1)) == 0;
 }
 
-// phase B: this warp scores candidates [lo, hi) of `pose` on its slice of the scan, JB candidates
-// at a time.  The last batch is padded by re-scoring candidate hi-1; padding results are not stored.
-template <int NPT, int JB, bool FAST_GEOM, int VAR>
-__device__ __forceinline__ void score_candidates(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* part, int lo,
-                                                 int hi, int NW, int warp, int lane) {
-  for (int j = lo; j < hi; j += JB) {
+// ---- thread-block cluster support -------------------------------------------------------------
+// A problem may be solved by a cluster of CL CTAs (one per SM) when the batch is too small to fill
+// the GPU: the CTAs are arranged as G candidate groups x S point slices (CL = G*S).  CTA (g, s)
+// keeps slice s of the scan in registers and scores the candidate batches assigned to group g.
+// Its warps' partial scores are first summed inside the CTA, then the CTA pushes one value per
+// candidate into the shared memory of ALL CTAs of the cluster (DSMEM stores); after one cluster
+// barrier every CTA holds every (candidate, slice) partial and runs phases A and C redundantly on
+// its own copy of the swarm (deterministic => identical in every CTA).
+struct Topo {
+  int CL, S, G;      // cluster size, point slices, candidate groups
+  int rank, s, g;    // this CTA
+  int NW, PW;        // warps per CTA; partials per candidate that phase C sums (NW when CL == 1, else S)
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v at the same shared-memory offset as `local` in CTA `rank` of this cluster
+__device__ __forceinline__ void st_cluster_f64(const double* local, unsigned rank, double v) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+}
+
+// phase B: this warp scores the candidates [lo, hi) of `pose` that belong to its CTA's group on its
+// slice of the scan, JB candidates at a time.  The last batch is padded by re-scoring candidate
+// hi-1; padding results are not stored.  wpart[j*NW + warp] receives this warp's partial.
+template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void score_candidates(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, int lo,
+                                                 int hi, const Topo& tp, int warp, int lane) {
+  for (int j = lo + tp.g * JB; j < hi; j += JB * tp.G) {
     double acc[JB];
     double2 txy[JB], cs[JB];
     bool weird = false;
@@ -260,28 +333,62 @@ __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double
     }
     const double tot = packed_warp_sum<JB>(acc, lane);
     const int jj = j + packed_slot<JB>(lane);
-    if (packed_writer<JB>(lane) && jj < hi) part[jj * NW + warp] = tot;
+    if (packed_writer<JB>(lane) && jj < hi) wpart[jj * tp.NW + warp] = tot;
   }
 }
 
-template <int NPT, int JB, bool FAST_GEOM, int VAR>
+// Cluster form, after phase B: sum the NW warp partials of every candidate this CTA scored and
+// store the sum into cpart[j*S + s] of every CTA of the cluster; one (candidate, destination) pair
+// per thread.  Ends with the cluster barrier that makes all partials visible everywhere.
+template <int JB, int CL>
+__device__ __forceinline__ void exchange_partials(const double* wpart, double* cpart, int lo, int hi, const Topo& tp) {
+  __syncthreads();
+  const int span = JB * tp.G;
+  const int mine = ((hi - lo + span - 1) / span) * JB;  // candidates of my group, padding included
+  for (int idx = threadIdx.x; idx < mine * CL; idx += blockDim.x) {
+    const int jl = idx / CL, dest = idx - jl * CL;
+    const int j = lo + tp.g * JB + (jl / JB) * span + (jl % JB);
+    if (j < hi) {
+      const double* p = wpart + j * tp.NW;
+      double c = 0.;
+      for (int w = 0; w < tp.NW; ++w) c += p[w];
+      st_cluster_f64(cpart + j * tp.S + tp.s, dest, c);
+    }
+  }
+  cluster_barrier();
+}
+
+// cost of candidate j = sum of its PW partials (slice-major, warp-minor) in a fixed 4-way interleaved
+// order: identical in every thread and CTA that asks, and short enough a dependency chain for phase C
+__device__ __forceinline__ double candidate_total(const double* part, int j, int PW) {
+  const double* p = part + j * PW;
+  double c0 = 0., c1 = 0., c2 = 0., c3 = 0.;
+  int w = 0;
+  for (; w + 4 <= PW; w += 4) {
+    c0 += p[w];
+    c1 += p[w + 1];
+    c2 += p[w + 2];
+    c3 += p[w + 3];
+  }
+  for (; w < PW; ++w) c0 += p[w];
+  return (c0 + c1) + (c2 + c3);
+}
+
+template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
 __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&pt)[NPT], const DevProblem& pr, const PsoParams& prm,
-                                            const SlicedSmem& sm, double* __restrict__ out, int* __restrict__ stats) {
-  const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5;
+                                            const SlicedSmem& sm, const Topo& tp, double* __restrict__ out, int* __restrict__ stats) {
+  const int tid = threadIdx.x, T = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int P = prm.P, I = prm.I;
+  const int P = prm.P, I = prm.I, PW = tp.PW;
   const int* __restrict__ rnd = pr.rnd;
+  NDTPSO_PHASE_DECL
   Pose* pose0 = sm.pose;
   Pose* pose1 = sm.pose + (P + 1);
+  // CL == 1: phase C sums the NW warp partials directly (double buffered).
+  // CL > 1 : warps write wpart (single buffer), exchange_partials() fills the double-buffered cpart.
   double* part0 = sm.partial;
-  double* part1 = sm.partial + (size_t)(P + 1) * NW;
-
-  // cost of candidate j = sum of its NW partials in warp order (identical in every thread that asks)
-  auto total = [&](const double* part, int j) {
-    double c = 0.;
-    for (int w = 0; w < NW; ++w) c += part[j * NW + w];
-    return c;
-  };
+  double* part1 = sm.partial + (size_t)(P + 1) * PW;
+  double* wpart = sm.wpart;
 
   // ---- initial swarm: task 0 = the seed particle (core.cpp:53,58), task 1+j = particle j (core.cpp:60-61)
   for (int t = tid; t < P + 1; t += T) {
@@ -296,9 +403,12 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     pose0[t] = Pose{pos[0], pos[1], c, s, pos[2], 0.};
   }
   __syncthreads();
-  score_candidates<NPT, JB, FAST_GEOM, VAR>(m, pt, pose0, part0, 0, P + 1, NW, warp, lane);
-  __syncthreads();
-  for (int t = tid; t < P + 1; t += T) sm.cost0[t] = total(part0, t);
+  score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose0, CL == 1 ? part0 : wpart, 0, P + 1, tp, warp, lane);
+  if (CL == 1)
+    __syncthreads();
+  else
+    exchange_partials<JB, CL>(wpart, part0, 0, P + 1, tp);
+  for (int t = tid; t < P + 1; t += T) sm.cost0[t] = candidate_total(part0, t, PW);
   __syncthreads();
   // every thread derives the initial gbest the way core.cpp:58-69 does (strict <, index order)
   double gbc = sm.cost0[0], gb0 = pose0[0].x, gb1 = pose0[0].y, gb2 = pose0[0].th;
@@ -326,6 +436,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
   // ---- iterations
   int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0;
   double w = prm.w;
+  NDTPSO_PHASE_MARK(0)
   while (it < I) {
     Pose* pose = par ? pose1 : pose0;
     double* part = par ? part1 : part0;
@@ -355,14 +466,20 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
       sm.vnew[3 * j + 2] = nv[2];
     }
     __syncthreads();
-    score_candidates<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, part, start, P, NW, warp, lane);  // phase B
-    __syncthreads();
+    NDTPSO_PHASE_MARK(1)
+    score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, P, tp, warp, lane);  // phase B
+    NDTPSO_PHASE_MARK(2)
+    if (CL == 1)
+      __syncthreads();
+    else
+      exchange_partials<JB, CL>(wpart, part, start, P, tp);
+    NDTPSO_PHASE_MARK(3)
     // phase C: j* = first pending particle that improves gbest (core.cpp:98)
     int jstar = -1;
     double cstar = 0.;
     for (int base = start; base < P && jstar < 0; base += 32) {
       const int j = base + lane;
-      const double cj = (j < P) ? total(part, j) : 0.;
+      const double cj = (j < P) ? candidate_total(part, j, PW) : 0.;
       const bool imp = (j < P) && (cj < gbc);
       const unsigned mask = __ballot_sync(0xffffffffu, imp);
       if (mask) {
@@ -374,7 +491,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     const int end = (jstar >= 0) ? jstar + 1 : P;
     for (int j = ja; j < end; j += T) {  // commit own particles in [start, end)  (core.cpp:89-96)
       const Pose ps = pose[j];
-      const double cj = total(part, j);
+      const double cj = candidate_total(part, j, PW);
       sm.x[3 * j] = ps.x;
       sm.x[3 * j + 1] = ps.y;
       sm.x[3 * j + 2] = ps.th;
@@ -403,9 +520,10 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     }
     par ^= 1;
     ++rounds;
+    NDTPSO_PHASE_MARK(4)
   }
 
-  if (tid == 0) {
+  if (tid == 0 && tp.rank == 0) {
     out[0] = gb0;
     out[1] = gb1;
     out[2] = gb2;
@@ -415,21 +533,22 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
       stats[1] = n_gb;
     }
   }
+  if (CL > 1) cluster_barrier();  // no CTA may exit while peers can still store into its shared memory
 }
 
 // Prologue shared by the production kernel and the phase-B microbenchmark: stages the compact
 // table with two bulk TMA copies, loads this thread's scan points into registers meanwhile
 // (coalesced 16-byte loads), and fills the loop-invariant context.
 template <int NPT>
-__device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, const DevProblem& pr, const DevMap& mp, int P, SliceCtx& m,
-                                                      double2 (&pt)[NPT]) {
+__device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, const DevProblem& pr, const DevMap& mp, int P, const Topo& tp,
+                                                      SliceCtx& m, double2 (&pt)[NPT]) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int n_rec = mp.hdr[HDR_NREC];
   const int row0 = mp.hdr[HDR_ROW0], nrows = mp.hdr[HDR_NROWS];
   const int span = nrows * mp.gw;
   const int rec_bytes = (n_rec + 1) * 48;
   const int grid_bytes = round16((span + 1) * 2);
-  const SlicedSmem sm = carve_sliced(smem_raw, P, T >> 5, rec_bytes + grid_bytes);
+  const SlicedSmem sm = carve_sliced(smem_raw, P, tp.PW, tp.CL == 1 ? 0 : tp.NW, rec_bytes + grid_bytes);
 
   if (tid < kExpTableSize) sm.etab[tid] = c_exp_table[tid];
   // constants go through volatile shared memory so the compiler keeps them in registers instead of
@@ -454,9 +573,10 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
     tma_load_1d(sm.table, mp.rec, rec_bytes, sm.bar);
     tma_load_1d(sm.table + rec_bytes, mp.grid, grid_bytes, sm.bar);
   }
+  // slice s of the scan: points k*(S*T) + s*T + tid
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
-    const int i = k * T + tid;
+    const int i = (k * tp.S + tp.s) * T + tid;
     pt[k] = (i < pr.n_pts) ? pr.pts[i] : make_double2(1e200, 0.);  // padding: out of bounds for every pose
   }
   m.rec = reinterpret_cast<const double*>(sm.table);
@@ -488,23 +608,40 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   return sm;
 }
 
-// Host guarantees: every table is compact and symmetric and fits prm.smem_bytes; n_pts <= NPT * blockDim.x.
-template <int NPT, int JB, int MAXT, int MINB>
+template <int CL>
+__device__ __forceinline__ Topo make_topo(int groups) {
+  Topo tp;
+  tp.CL = CL;
+  tp.G = (CL == 1) ? 1 : groups;
+  tp.S = CL / tp.G;
+  tp.rank = (CL == 1) ? 0 : static_cast<int>(cluster_ctarank());
+  tp.s = tp.rank % tp.S;
+  tp.g = tp.rank / tp.S;
+  tp.NW = blockDim.x >> 5;
+  tp.PW = (CL == 1) ? tp.NW : tp.S;
+  return tp;
+}
+
+// Host guarantees: every table is compact and symmetric and fits the dynamic shared memory;
+// n_pts <= NPT * S * blockDim.x; the grid is n_problems * CL CTAs launched as clusters of CL.
+template <int NPT, int JB, int CL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem* __restrict__ probs, const DevMap* __restrict__ maps,
-                                                              PsoParams prm, double* __restrict__ out, int* __restrict__ stats) {
+                                                              PsoParams prm, int groups, double* __restrict__ out, int* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / CL;
   const DevProblem& pr = probs[b];
   const DevMap& mp = maps[pr.map_id];
+  const Topo tp = make_topo<CL>(groups);
   SliceCtx m;
   double2 pt[NPT];
-  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, m, pt);
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt);
+  if (CL > 1) cluster_barrier();  // every CTA's shared memory is carved before anyone stores into it
   double* o = out + 4 * (size_t)b;
   int* s = stats ? stats + 2 * (size_t)b : nullptr;
   if (mp.fast_geom)
-    sliced_body<NPT, JB, true, kProdVariant>(m, pt, pr, prm, sm, o, s);
+    sliced_body<NPT, JB, CL, true, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
   else
-    sliced_body<NPT, JB, false, kProdVariant>(m, pt, pr, prm, sm, o, s);
+    sliced_body<NPT, JB, CL, false, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
 }
 
 // Phase-B microbenchmark: every CTA stages problem blockIdx.x % n_problems and scores `ncand`
@@ -515,9 +652,10 @@ __global__ void __launch_bounds__(MAXT, MINB) score_bench_kernel(const DevProble
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevProblem& pr = probs[blockIdx.x % n_problems];
   const DevMap& mp = maps[pr.map_id];
+  const Topo tp = make_topo<1>(1);
   SliceCtx m;
   double2 pt[NPT];
-  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, ncand - 1, m, pt);
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, ncand - 1, tp, m, pt);
   const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5, warp = tid >> 5, lane = tid & 31;
   for (int j = tid; j < ncand; j += T) {
     const double th = pr.guess[2] + 1e-3 * (j % 17 - 8);
@@ -528,9 +666,9 @@ __global__ void __launch_bounds__(MAXT, MINB) score_bench_kernel(const DevProble
   __syncthreads();
   for (int r = 0; r < reps; ++r) {
     if (mp.fast_geom)
-      score_candidates<NPT, JB, true, VAR>(m, pt, sm.pose, sm.partial, 0, ncand, NW, warp, lane);
+      score_candidates<NPT, JB, 1, true, VAR>(m, pt, sm.pose, sm.partial, 0, ncand, tp, warp, lane);
     else
-      score_candidates<NPT, JB, false, VAR>(m, pt, sm.pose, sm.partial, 0, ncand, NW, warp, lane);
+      score_candidates<NPT, JB, 1, false, VAR>(m, pt, sm.pose, sm.partial, 0, ncand, tp, warp, lane);
     __syncthreads();
   }
   if (tid == 0) {

@@ -191,3 +191,23 @@ def test_asymmetric_inverse_covariance(oracle, ctx):
     pose, cost = ctx.align_batch([flat], capi.PsoConfig.make(population=16, iterations=8))
     po, co, _ = oracle.pso(flat, flat["guess"], flat["deviation"], 16, 8, seed=4)
     assert np.abs(pose[0] - po).max() <= POSE_ATOL and rel_err(cost[0], co) <= SCORE_RTOL
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_cluster_sizes(golden, cluster):
+    """Small batches spread each problem over a thread-block cluster (DSMEM exchange of the partial
+    scores); every cluster size must reproduce the reference."""
+    c = capi.Context(0)
+    c.set_option(capi.OPT_CLUSTER, cluster)
+    try:
+        for case, inputs, take in [("cfg2", "cfg2", 2), ("cfg1", "cfg1", 3), ("align_default", "align_default", 1),
+                                   ("edge_one_particle", "edge", 2), ("edge_empty_scan", "edge", 1), ("np2", "np2", 2)]:
+            cs, flats = golden.problems(case, inputs)
+            flats = flats[:take]
+            if case == "edge_empty_scan":
+                flats = [empty_points(f) for f in flats]
+            pose, cost = c.align_batch(flats, conf_of(cs))
+            assert np.abs(pose - cs["pose"][:take]).max() <= POSE_ATOL, (case, cluster)
+            assert rel_err(cost, cs["cost"][:take]).max() <= SCORE_RTOL, (case, cluster)
+    finally:
+        c.close()

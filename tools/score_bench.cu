@@ -1,6 +1,7 @@
 // Phase-B microbenchmark library (tools only; not part of the product build).
 // Builds the whole C ABI plus ndtpso_bench_score(), which times score_bench_kernel for one
 // (points-per-thread, candidate-batch, launch-bounds, code variant) configuration.
+#define NDTPSO_PHASE_TIMING 1
 #include "../ndtpso_slam_b200/csrc/ndtpso_capi.cu"
 
 namespace {
@@ -8,7 +9,7 @@ template <int NPT, int JB, int VAR, int MAXT, int MINB>
 int run_cfg(ndtpso_batch* bt, int nw, int grid, int ncand, int reps, double* out_ms, int* out_regs, int* out_ctas_per_sm) {
   ndtpso_ctx* ctx = bt->ctx;
   auto kern = score_bench_kernel<NPT, JB, VAR, MAXT, MINB>;
-  const int smem = round16(sliced_smem_bytes(ncand - 1, nw, bt->max_table_smem));
+  const int smem = round16(sliced_smem_bytes(ncand - 1, nw, 0, bt->max_table_smem));  // PW = nw (one CTA per problem)
   CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
   cudaFuncAttributes fa;
   CUDA_TRY(ctx, cudaFuncGetAttributes(&fa, kern));
@@ -79,4 +80,12 @@ extern "C" int ndtpso_bench_score(ndtpso_ctx* ctx, int32_t n, const ndtpso_probl
   out_info[3] = occ;
   ndtpso_batch_destroy(bt);
   return rc;
+}
+
+// cycles summed over CTAs: [0] prologue+init, [1] phase A (+ barrier), [2] phase B (thread 0's own scoring), [3] wait at the barrier
+// after B, [4] phase C; reset != 0 clears the counters first
+extern "C" int ndtpso_bench_phase_cycles(unsigned long long* out, int reset) {
+  unsigned long long z[8] = {0};
+  if (reset) return cudaMemcpyToSymbol(ndtpso::g_phase_cycles, z, sizeof z) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(out, ndtpso::g_phase_cycles, sizeof z) == cudaSuccess ? 0 : -2;
 }

@@ -117,7 +117,8 @@ enum {
   NDTPSO_OPT_CLUSTER = 3,       /* CTAs cooperating on one problem; 0 = auto */
   NDTPSO_OPT_KERNEL = 4,        /* 0 = auto, 1 = warp-per-particle (generic), 2 = point-sliced */
   NDTPSO_OPT_POINTS_PER_THREAD = 5, /* point-sliced kernel: scan points held per thread; 0 = auto */
-  NDTPSO_OPT_CANDIDATE_BATCH = 6   /* point-sliced kernel: candidates scored together (1, 2, 4); 0 = auto */
+  NDTPSO_OPT_CANDIDATE_BATCH = 6,  /* point-sliced kernel: candidates scored together (1, 2, 4); 0 = auto */
+  NDTPSO_OPT_PIPELINE_CHUNKS = 7   /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4, default 1) */
 };
 int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value);
 
@@ -131,6 +132,13 @@ int64_t ndtpso_rand_draws(const ndtpso_pso_config* conf);
  * global_best.best_cost (the reference only prints it, core.cpp:111-114). out_cost may be NULL. */
 int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf,
                        double* out_pose /* [n][3] */, double* out_cost /* [n] */);
+
+/* The same call split in two so that a throughput-oriented caller can overlap the host-side staging
+ * of batch k+1 with the GPU work of batch k:  submit = stage + H2D + kernel launches (asynchronous),
+ * collect = D2H of the poses + synchronise + release.  Batches submitted on one context complete in
+ * submission order. */
+int ndtpso_align_submit(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out);
+int ndtpso_align_collect(ndtpso_batch* batch, double* out_pose /* [n][3] */, double* out_cost /* [n] */);
 
 /* Replaces cost_function (core.h:49-50): cost of `n_poses` candidate poses per problem. */
 int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int32_t n_poses,

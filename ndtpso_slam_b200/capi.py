@@ -14,13 +14,13 @@ import numpy as np
 from . import build as _build
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_LIMIT = 0, -1, -2, -3, -4, -5
-OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREAD, OPT_CANDIDATE_BATCH = 1, 2, 3, 4, 5, 6
+OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREAD, OPT_CANDIDATE_BATCH, OPT_PIPELINE_CHUNKS = 1, 2, 3, 4, 5, 6, 7
 KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 
 #: every symbol include/ndtpso_b200.h declares
 EXPORTS = [
     "ndtpso_abi_version", "ndtpso_pso_config_default", "ndtpso_device_count", "ndtpso_ctx_create", "ndtpso_ctx_destroy",
-    "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch",
+    "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch", "ndtpso_align_submit", "ndtpso_align_collect",
     "ndtpso_cost_batch", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
     "ndtpso_batch_stats", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
 ]
@@ -81,6 +81,8 @@ def load_library(build_if_missing: bool = True):
     L.ndtpso_rand_draws.argtypes = [C.POINTER(PsoConfig)]
     L.ndtpso_rand_draws.restype = C.c_int64
     L.ndtpso_align_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.c_void_p, C.c_void_p]
+    L.ndtpso_align_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
+    L.ndtpso_align_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndtpso_cost_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.c_int32, C.c_void_p, C.c_void_p]
     L.ndtpso_batch_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
     L.ndtpso_batch_solve.argtypes = [C.c_void_p]
@@ -228,6 +230,19 @@ class Context:
         pose = np.empty((ps.n, 3), dtype=np.float64)
         cost = np.empty(ps.n, dtype=np.float64)
         self._check(self.lib.ndtpso_align_batch(self.h, ps.n, ps.array, C.byref(conf), _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def align_submit(self, problems: "ProblemSet", conf: PsoConfig):
+        """Asynchronous half of align_batch: stage + H2D + launches.  Returns a ticket for align_collect."""
+        h = C.c_void_p()
+        self._check(self.lib.ndtpso_align_submit(self.h, problems.n, problems.array, C.byref(conf), C.byref(h)))
+        return (h, problems.n)
+
+    def align_collect(self, ticket):
+        h, n = ticket
+        pose = np.empty((n, 3), dtype=np.float64)
+        cost = np.empty(n, dtype=np.float64)
+        self._check(self.lib.ndtpso_align_collect(h, _ptr(pose), _ptr(cost)))
         return pose, cost
 
     def cost_batch(self, flats, poses):

@@ -40,12 +40,15 @@ struct ndtpso_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // pipelined align_batch
+  cudaStream_t copy_stream = nullptr;  // uploads of batch k+1 overlap the kernels of batch k
   std::string err;
   int opt_warps = 0;
   int64_t opt_smem = 0;
   int opt_cluster = 0;
   int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
+  int opt_chunks = 1;      // pipelined align_batch: number of chunks (1 = off)
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the most recent upload / results call
@@ -73,6 +76,10 @@ struct ndtpso_batch {
   bool all_compact = true;  // every table has <= 65534 built cells
   bool all_symmetric = true;  // every built cell has S01 == S10 bit for bit (NDTCell::build always does)
   bool solved = false;
+  bool results_enqueued = false;  // align_submit already queued the D2H of the results behind the kernels
+  cudaEvent_t ev_done = nullptr;
+  cudaEvent_t ev_up = nullptr;  // upload finished (copy stream)
+  bool no_cluster = false;  // chunk of a pipelined align_batch: the chunks together fill the GPU
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around K0, K1, K2 of the last solve
 };
 
@@ -114,7 +121,7 @@ int pool_take(ndtpso_ctx* ctx, std::vector<PoolBuf>& pool, size_t bytes, bool pi
 
 void pool_give(std::vector<PoolBuf>& pool, PoolBuf b, bool pinned) {
   if (!b.ptr) return;
-  if (pool.size() >= 4) {  // keep the pool small: drop the smallest
+  if (pool.size() >= 8) {  // keep the pool small: drop the smallest
     int small = 0;
     for (int i = 1; i < (int)pool.size(); ++i)
       if (pool[i].bytes < pool[small].bytes) small = i;
@@ -456,7 +463,17 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
 
 int batch_upload(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
-  CUDA_TRY(ctx, cudaMemcpyAsync(bt->dev.ptr, bt->pin.ptr, bt->upload_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->stream == ctx->own_stream) {
+    // own stream: upload on the copy stream so that it overlaps kernels of earlier batches; the
+    // compute stream waits for it (the arena of an in-flight batch is never reused, see the pool)
+    if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!bt->ev_up) CUDA_TRY(ctx, cudaEventCreateWithFlags(&bt->ev_up, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaMemcpyAsync(bt->dev.ptr, bt->pin.ptr, bt->upload_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(bt->ev_up, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, bt->ev_up, 0));
+  } else {
+    CUDA_TRY(ctx, cudaMemcpyAsync(bt->dev.ptr, bt->pin.ptr, bt->upload_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
   ctx->last_h2d = (int64_t)bt->upload_bytes;
   return NDTPSO_OK;
 }
@@ -587,7 +604,7 @@ int launch_sliced(ndtpso_batch* bt) {
       default: rc = try_cluster<16>(bt, true); break;
     }
     if (rc != 1) return rc;
-  } else if (ctx->opt_cluster == 0 && bt->n * 2 <= ctx->sm_count) {
+  } else if (ctx->opt_cluster == 0 && !bt->no_cluster && bt->n * 2 <= ctx->sm_count) {
     int rc = 1;
     if (bt->n * 16 <= ctx->sm_count) rc = try_cluster<16>(bt, false);
     if (rc == 1 && bt->n * 8 <= ctx->sm_count) rc = try_cluster<8>(bt, false);
@@ -704,6 +721,9 @@ void ndtpso_ctx_destroy(ndtpso_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->dev_pool) cudaFree(b.ptr);
   for (auto& b : ctx->pin_pool) cudaFreeHost(b.ptr);
+  for (auto& cs : ctx->chunk_stream)
+    if (cs) cudaStreamDestroy(cs);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -726,6 +746,10 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
     case NDTPSO_OPT_KERNEL:
       if (value < 0 || value > 2) return fail(ctx, NDTPSO_ERR_ARG, "kernel must be 0 (auto), 1 (warp-per-particle) or 2 (point-sliced)");
       ctx->opt_kernel = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_PIPELINE_CHUNKS:
+      if (value < 1 || value > 4) return fail(ctx, NDTPSO_ERR_ARG, "pipeline chunks must be in 1..4");
+      ctx->opt_chunks = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_CANDIDATE_BATCH:
       if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NDTPSO_ERR_ARG, "candidate batch must be 0, 1, 2 or 4");
@@ -845,8 +869,12 @@ int ndtpso_batch_results(ndtpso_batch* bt, double* out_pose, double* out_cost) {
   if (bt->n == 0) return NDTPSO_OK;
   // results come back through the (already consumed) head of the pinned staging buffer
   double* h = static_cast<double*>(bt->pin.ptr);
-  CUDA_TRY(ctx, cudaMemcpyAsync(h, bt->d_out, sizeof(double) * 4 * (size_t)bt->n, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (bt->results_enqueued) {
+    CUDA_TRY(ctx, cudaEventSynchronize(bt->ev_done));  // waits for THIS batch only, not for batches queued behind it
+  } else {
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, bt->d_out, sizeof(double) * 4 * (size_t)bt->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   ctx->last_d2h = (int64_t)sizeof(double) * 4 * bt->n;
   for (int b = 0; b < bt->n; ++b) {
     if (out_pose) {
@@ -873,7 +901,12 @@ void ndtpso_batch_destroy(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   if (ctx) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);  // nothing in flight may still read the buffers
+    if (bt->results_enqueued && bt->solved)
+      cudaEventSynchronize(bt->ev_done);  // this batch is finished; batches queued behind it keep running
+    else
+      cudaStreamSynchronize(ctx->stream);  // nothing in flight may still read the buffers
+    if (bt->ev_done) cudaEventDestroy(bt->ev_done);
+    if (bt->ev_up) cudaEventDestroy(bt->ev_up);
     pool_give(ctx->dev_pool, bt->dev, false);
     pool_give(ctx->pin_pool, bt->pin, true);
     for (auto& e : bt->ev)
@@ -885,12 +918,81 @@ void ndtpso_batch_destroy(ndtpso_batch* bt) {
 int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, double* out_pose,
                        double* out_cost) {
   if (!ctx || !conf || (n > 0 && !out_pose)) return fail(ctx, NDTPSO_ERR_ARG, "align_batch: null argument");
+  // Large batches on the context's own stream are pipelined: the batch is cut into up to 4 chunks,
+  // each staged (host scan + pack of the built cells), uploaded and launched on its own stream, so
+  // the host stages chunk k+1 while the GPU already works on chunk k.  Results are identical to the
+  // one-shot path (a problem's result does not depend on the batch it is in).
+  const int chunks = (ctx->stream == ctx->own_stream && n >= 64) ? std::min(ctx->opt_chunks, n / 32) : 1;
+  if (chunks <= 1) {
+    ndtpso_batch* bt = nullptr;
+    int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // built cells only cross PCIe
+    if (rc) return rc;
+    rc = ndtpso_batch_solve(bt);
+    if (rc == NDTPSO_OK) rc = ndtpso_batch_results(bt, out_pose, out_cost);
+    ndtpso_batch_destroy(bt);
+    return rc;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ndtpso_batch* bts[4] = {nullptr, nullptr, nullptr, nullptr};
+  int lo[5];
+  for (int k = 0; k <= chunks; ++k) lo[k] = (int)((int64_t)n * k / chunks);
+  int rc = NDTPSO_OK;
+  int64_t h2d = 0;
+  cudaStream_t saved = ctx->stream;
+  for (int k = 0; k < chunks && rc == NDTPSO_OK; ++k) {
+    if (!ctx->chunk_stream[k] && cudaStreamCreateWithFlags(&ctx->chunk_stream[k], cudaStreamNonBlocking) != cudaSuccess) {
+      rc = fail(ctx, NDTPSO_ERR_CUDA, "cudaStreamCreateWithFlags failed");
+      break;
+    }
+    ctx->stream = ctx->chunk_stream[k];
+    rc = batch_create_impl(ctx, lo[k + 1] - lo[k], problems + lo[k], conf, true, &bts[k]);
+    if (rc == NDTPSO_OK) {
+      h2d += ctx->last_h2d;
+      bts[k]->no_cluster = true;
+      rc = ndtpso_batch_solve(bts[k]);
+    }
+  }
+  for (int k = 0; k < chunks; ++k) {
+    if (!bts[k]) continue;
+    ctx->stream = ctx->chunk_stream[k];
+    if (rc == NDTPSO_OK) rc = ndtpso_batch_results(bts[k], out_pose + 3 * (size_t)lo[k], out_cost ? out_cost + lo[k] : nullptr);
+    ndtpso_batch_destroy(bts[k]);
+  }
+  ctx->stream = saved;
+  ctx->last_h2d = h2d;
+  ctx->last_d2h = (int64_t)sizeof(double) * 4 * n;
+  return rc;
+}
+
+int ndtpso_align_submit(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out) {
+  if (!ctx || !conf || !out) return fail(ctx, NDTPSO_ERR_ARG, "align_submit: null argument");
+  *out = nullptr;
   ndtpso_batch* bt = nullptr;
-  int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // built cells only cross PCIe
+  int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // stage (built cells only) + asynchronous H2D
   if (rc) return rc;
-  rc = ndtpso_batch_solve(bt);
-  if (rc == NDTPSO_OK) rc = ndtpso_batch_results(bt, out_pose, out_cost);
-  ndtpso_batch_destroy(bt);
+  rc = ndtpso_batch_solve(bt);  // asynchronous launches
+  if (rc == NDTPSO_OK && bt->n > 0) {
+    // queue the read-back right behind the kernels (the head of the staging buffer is free again:
+    // the upload it held completed before the kernels started) and mark the batch's completion
+    cudaError_t e = cudaEventCreateWithFlags(&bt->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(bt->pin.ptr, bt->d_out, sizeof(double) * 4 * (size_t)bt->n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(bt->ev_done, ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e));
+    bt->results_enqueued = (rc == NDTPSO_OK);
+  }
+  if (rc) {
+    ndtpso_batch_destroy(bt);
+    return rc;
+  }
+  *out = bt;
+  return NDTPSO_OK;
+}
+
+int ndtpso_align_collect(ndtpso_batch* batch, double* out_pose, double* out_cost) {
+  if (!batch) return NDTPSO_ERR_ARG;
+  const int rc = ndtpso_batch_results(batch, out_pose, out_cost);
+  ndtpso_batch_destroy(batch);
   return rc;
 }
 

@@ -211,3 +211,15 @@ def test_cluster_sizes(golden, cluster):
             assert rel_err(cost, cs["cost"][:take]).max() <= SCORE_RTOL, (case, cluster)
     finally:
         c.close()
+
+
+def test_submit_collect_pipelined(golden, ctx):
+    """ndtpso_align_submit / ndtpso_align_collect with several batches in flight == ndtpso_align_batch."""
+    c, flats = golden.problems("cfg1")
+    cf = conf_of(c)
+    want_pose, want_cost = ctx.align_batch(flats, cf)
+    sets = [capi.ProblemSet(flats[i::3]) for i in range(3)]
+    tickets = [ctx.align_submit(ps, cf) for ps in sets]
+    for i, t in enumerate(tickets):
+        pose, cost = ctx.align_collect(t)
+        assert np.array_equal(pose, want_pose[i::3]) and np.array_equal(cost, want_cost[i::3])

@@ -74,7 +74,7 @@ struct ndtpso_batch {
   int max_pts = 0;        // largest scan
   int max_table_smem = 0; // records + grid of the largest table
   bool all_compact = true;  // every table has <= 65534 built cells
-  bool all_symmetric = true;  // every built cell has S01 == S10 bit for bit (NDTCell::build always does)
+  bool all_symmetric = true;  // every built cell: S01 == S10 bit for bit, finite, positive semi-definite (NDTCell::build always does)
   bool solved = false;
   bool results_enqueued = false;  // align_submit already queued the D2H of the results behind the kernels
   cudaEvent_t ev_done = nullptr;
@@ -201,7 +201,7 @@ void parallel_for(int n, int max_threads, F f) {
 struct MapScan {
   std::vector<int> cells;  // built cell indices, ascending (dense input); empty for sparse input
   int n_rec = 0, row0 = 0, nrows = 0;
-  bool symmetric = true, ok = true;
+  bool symmetric = true, ok = true;  // symmetric: also finite and positive semi-definite
 };
 
 void scan_map(const ndtpso_map_view& m, bool want_cells, MapScan* out) {
@@ -212,7 +212,12 @@ void scan_map(const ndtpso_map_view& m, bool want_cells, MapScan* out) {
     ay = std::min(ay, iy);
     by = std::max(by, iy);
     ++n_rec;
-    if (memcmp(&m.inv_cov[4 * row + 1], &m.inv_cov[4 * row + 2], sizeof(double)) != 0) out->symmetric = false;
+    const double* S = &m.inv_cov[4 * row];
+    if (memcmp(&S[1], &S[2], sizeof(double)) != 0) out->symmetric = false;
+    // finite and positive semi-definite (NaN/inf fail the comparisons): the sliced kernel's exponent is then <= 0
+    if (!(S[0] >= 0. && S[3] >= 0. && S[0] * S[3] - S[1] * S[2] >= 0. && S[0] < 1e300 && S[3] < 1e300 && std::isfinite(m.mean[2 * row]) &&
+          std::isfinite(m.mean[2 * row + 1])))
+      out->symmetric = false;
   };
   if (m.n_sparse >= 0) {
     for (int r = 0; r < m.n_sparse; ++r) {

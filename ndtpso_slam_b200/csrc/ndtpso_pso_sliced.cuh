@@ -63,6 +63,7 @@ struct SlicedSmem {
   Pose* pose;       // [2][P+1]
   double* partial;  // [2][(P+1)*PW]
   double* wpart;    // [(P+1)*NW] warp partials of the cluster form (unused when CL == 1)
+  double* ubuf;     // [2][6P] |Random()| coefficients of the current / next iteration (core.cpp:84)
   double* cost0;    // [P+1] initial costs
   double* x;        // [P][3]  owner-private particle state
   double* v;        // [P][3]
@@ -77,6 +78,7 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   int b = 2 * (P + 1) * (int)sizeof(Pose);
   b += 2 * (P + 1) * PW * (int)sizeof(double);
   b += (P + 1) * WP * (int)sizeof(double);
+  b += 2 * 6 * Pn * (int)sizeof(double);
   b += (P + 1) * (int)sizeof(double);
   b += Pn * 13 * (int)sizeof(double);
   return (b + 15) & ~15;
@@ -100,6 +102,8 @@ __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, i
   p += 2 * (size_t)(P + 1) * PW * sizeof(double);
   s.wpart = reinterpret_cast<double*>(p);
   p += (size_t)(P + 1) * WP * sizeof(double);
+  s.ubuf = reinterpret_cast<double*>(p);
+  p += 2 * 6 * (size_t)Pn * sizeof(double);
   s.cost0 = reinterpret_cast<double*>(p);
   p += (P + 1) * sizeof(double);
   double* d = reinterpret_cast<double*>(p);
@@ -125,12 +129,11 @@ struct SliceCtx {
 // inside the frame (strict), its cell is built, and the value is a normal double (>= 2.2e-308;
 // smaller ones are flushed to zero, see fast_exp.h).  Padding points of the last slice are stored
 // as (1e200, 0): whatever the pose, |x'| or |y'| is then ~1e200, i.e. out of bounds, so they need
-// no validity flag.  `weird` is raised when the exponent is > 709, +inf or NaN -- only an indefinite
-// or non-finite "inverse covariance" can do that -- and the caller then re-scores the candidate
-// with slice_point_exact so that such inputs behave like the reference.
+// no validity flag.  The host only selects this kernel for tables whose every Sigma^-1 is finite,
+// symmetric and positive semi-definite (what NDTCell::build produces), so the exponent is <= 0 up
+// to rounding and can never overflow; anything else takes the generic kernel (library exp).
 template <bool FAST_GEOM, int VAR>
-__device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, double tx, double ty, double c, double s, double& acc,
-                                            bool& weird) {
+__device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, double tx, double ty, double c, double s, double& acc) {
   const double x = fma(p.x, c, fma(-p.y, s, tx));  // transform_point, core.h:29-30
   const double y = fma(p.x, s, fma(p.y, c, ty));
   bool inb;
@@ -186,25 +189,6 @@ __device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, 
   const int ehi = use ? __double2hiint(val) + ((k >> kExpTableShift) << 20) : 0;
   const int elo = use ? __double2loint(val) : 0;
   acc -= __hiloint2double(ehi, elo);
-  weird = weird || (use && ahi > 0x40862800);
-}
-
-// Exact (library exp, branchy) version of the same point, for the rare `weird` candidates.
-__device__ __noinline__ double slice_point_exact(const SliceCtx& m, const double2 p, double tx, double ty, double c, double s) {
-  const double x = fma(p.x, c, fma(-p.y, s, tx));
-  const double y = fma(p.x, s, fma(p.y, c, ty));
-  if (!((x > m.x_min) && (x < m.x_max) && (y > m.y_min) && (y < m.y_max))) return 0.;
-  const int ix = __double2int_rd(__ddiv_rn(x + m.hw, m.cs)), iy = __double2int_rd(__ddiv_rn(y + m.hh, m.cs));
-  const unsigned g = static_cast<unsigned>(ix + m.gw * iy - m.base);
-  if (g >= static_cast<unsigned>(m.span)) return 0.;
-  const unsigned r = m.grid[g];
-  if (r == static_cast<unsigned>(m.null_id)) return 0.;
-  const double* q = m.rec + 6 * r;
-  const double d0 = x - q[0], d1 = y - q[1];
-  const double r0 = fma(d1, q[3], d0 * q[2]);
-  const double r1 = fma(d1, q[5], d0 * q[3]);
-  const double a = fma(r1, d1, r0 * d0);
-  return (a < -708.0) ? 0. : exp(a);
 }
 
 // Packed warp reduction of JB per-lane accumulators (one per candidate): after it, the total of
@@ -310,7 +294,6 @@ __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double
   for (int j = lo + tp.g * JB; j < hi; j += JB * tp.G) {
     double acc[JB];
     double2 txy[JB], cs[JB];
-    bool weird = false;
 #pragma unroll
     for (int b = 0; b < JB; ++b) {
       const Pose* ps = pose + min(j + b, hi - 1);
@@ -321,15 +304,7 @@ __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double
 #pragma unroll
     for (int b = 0; b < JB; ++b) {
 #pragma unroll
-      for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b], weird);
-    }
-    if (__any_sync(0xffffffffu, weird)) {  // never taken for tables NDTCell::build can produce
-#pragma unroll
-      for (int b = 0; b < JB; ++b) {
-        acc[b] = 0.;
-#pragma unroll 1
-        for (int k = 0; k < NPT; ++k) acc[b] -= slice_point_exact(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y);
-      }
+      for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b]);
     }
     const double tot = packed_warp_sum<JB>(acc, lane);
     const int jj = j + packed_slot<JB>(lane);
@@ -389,6 +364,14 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
   double* part0 = sm.partial;
   double* part1 = sm.partial + (size_t)(P + 1) * PW;
   double* wpart = sm.wpart;
+  // the 6P velocity coefficients of iteration `iter` -> ubuf[iter & 1]; issued right before a scoring
+  // phase so that the global-memory latency and the conversions hide behind it
+  auto prefetch_draws = [&](int iter) {
+    if (iter >= I) return;
+    double* dst = sm.ubuf + (iter & 1) * 6 * P;
+    const int* src = rnd + 3 + 3 * P + 6 * P * iter;
+    for (int i = tid; i < 6 * P; i += T) dst[i] = fabs(unit_random(src[i]));  // Array2d::Random().abs(), core.cpp:84
+  };
 
   // ---- initial swarm: task 0 = the seed particle (core.cpp:53,58), task 1+j = particle j (core.cpp:60-61)
   for (int t = tid; t < P + 1; t += T) {
@@ -403,6 +386,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     pose0[t] = Pose{pos[0], pos[1], c, s, pos[2], 0.};
   }
   __syncthreads();
+  prefetch_draws(0);
   score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose0, CL == 1 ? part0 : wpart, 0, P + 1, tp, warp, lane);
   if (CL == 1)
     __syncthreads();
@@ -442,14 +426,14 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     double* part = par ? part1 : part0;
     // phase A: owners of the pending particles [start, P)
     const int ja = start + ((tid - start) % T + T) % T;  // first pending particle owned by this thread
+    const double* ucoef = sm.ubuf + (it & 1) * 6 * P;
     for (int j = ja; j < P; j += T) {
-      const int base = 3 + 3 * P + 6 * P * it + 6 * j;
       double nx[3], nv[3];
       const double gb[3] = {gb0, gb1, gb2};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const double rx = fabs(unit_random(rnd[base + 2 * k]));  // Array2d::Random().abs(), core.cpp:84
-        const double ry = fabs(unit_random(rnd[base + 2 * k + 1]));
+        const double rx = ucoef[6 * j + 2 * k];  // draw 3+3P + 6P*it + 6j + 2k (and +1), prefetched
+        const double ry = ucoef[6 * j + 2 * k + 1];
         const double xk = sm.x[3 * j + k], vk = sm.v[3 * j + k], pbk = sm.pb[3 * j + k];
         // core.cpp:85-87: ((w*v) + ((c1*rx)*(pb-x))) + ((c2*ry)*(gb-x)), no contraction
         const double t1 = __dmul_rn(w, vk);
@@ -467,6 +451,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     }
     __syncthreads();
     NDTPSO_PHASE_MARK(1)
+    if (start == 0) prefetch_draws(it + 1);  // first round of an iteration
     score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, P, tp, warp, lane);  // phase B
     NDTPSO_PHASE_MARK(2)
     if (CL == 1)

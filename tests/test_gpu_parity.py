@@ -223,3 +223,44 @@ def test_submit_collect_pipelined(golden, ctx):
     for i, t in enumerate(tickets):
         pose, cost = ctx.align_collect(t)
         assert np.array_equal(pose, want_pose[i::3]) and np.array_equal(cost, want_cost[i::3])
+
+
+def test_indefinite_inverse_covariance(oracle, ctx):
+    """A symmetric but indefinite "Sigma^-1" makes the exponent positive; the library must take the
+    exact (library exp) kernel and agree with the oracle."""
+    rng = np.random.default_rng(12)
+    gw = gh = 16
+    n = gw * gh
+    built = np.ones(n, dtype=np.uint8)
+    mean = np.stack([(np.arange(n) % gw + 0.5) - 8.0, (np.arange(n) // gw + 0.5) - 8.0], 1)
+    off = rng.uniform(3, 5, n)
+    icov = np.stack([rng.uniform(1, 2, n), off, off, rng.uniform(1, 2, n)], 1)  # det < 0
+    flat = dict(points=rng.uniform(-7, 7, size=(200, 2)), mean=mean, inv_cov=icov, built=built, w_cells=gw, h_cells=gh,
+                width_m=16.0, height_m=16.0, cell_side=1.0, x_min=-8.0, x_max=8.0, y_min=-8.0, y_max=8.0,
+                guess=(0.1, 0.1, 0.01), deviation=(0.2, 0.2, 0.02), seed=6)
+    pose, cost = ctx.align_batch([flat], capi.PsoConfig.make(population=10, iterations=6))
+    po, co, _ = oracle.pso(flat, flat["guess"], flat["deviation"], 10, 6, seed=6)
+    assert np.abs(pose[0] - po).max() <= POSE_ATOL and rel_err(cost[0], co) <= SCORE_RTOL
+
+
+def test_cfg3_batch_against_oracle(oracle, ctx):
+    """BASELINE.json configs[2]: a batch of 256 trajectory problems (own table each), 70 x 50.
+    Every result is finite and near the true pose; a sample of them is checked against the oracle."""
+    from ndtpso_slam_b200 import synthetic as syn, workload
+    flats = workload.cfg2_batch(256)
+    cf = capi.PsoConfig.make(population=70, iterations=50)
+    pose, cost = ctx.align_batch(flats, cf)
+    assert np.isfinite(pose).all() and (cost < -300).all()
+    for b in (0, 1, 37, 128, 255):
+        po, co, _ = oracle.pso(flats[b], flats[b]["guess"], flats[b]["deviation"], 70, 50, seed=flats[b]["seed"])
+        assert np.abs(pose[b] - po).max() <= POSE_ATOL, b
+        assert rel_err(cost[b], co) <= SCORE_RTOL, b
+    # idempotence / determinism at full size: the same batch again, and as two halves
+    pose2, cost2 = ctx.align_batch(flats, cf)
+    assert np.array_equal(pose, pose2) and np.array_equal(cost, cost2)
+    a = ctx.align_batch(flats[:128], cf)
+    assert np.array_equal(a[0], pose[:128])
+    # the matcher converges: most results are within 2 cm / 0.2 deg of the true pose of the synthetic scene
+    truth = np.array([syn.trajectory_problem(syn.CFG2, b).true_pose for b in range(256)])
+    err = np.abs(pose - truth)
+    assert np.median(err[:, :2].max(axis=1)) < 0.02 and np.median(err[:, 2]) < 0.004

@@ -181,6 +181,16 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def measured_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of pso_sliced_kernel per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/); None for a batch size that was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(str(batch))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -314,6 +324,25 @@ def run_gpu_arm(args):
     fp64_peak = ctx.fp64_peak_tflops()
     bt.close()
 
+    # ---- configs[1] read literally: ONE scan-match at a time (thread-block-cluster form of the kernel)
+    single = None
+    if rank == 0:
+        one = capi.ProblemSet(pinned_flats[:1])
+        b1 = ctx.batch(one, conf)
+        ks = []
+        for _ in range(args.warmup + 10):
+            b1.solve()
+            ks.append(float(b1.kernel_times_ms().sum()))
+        b1.close()
+        for _ in range(3):
+            ctx.align_batch(one, conf)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ctx.align_batch(one, conf)
+        lat = (time.perf_counter() - t0) / 20
+        single = {"resident_ms": float(np.median(ks[args.warmup:])), "e2e_ms": 1e3 * lat, "e2e_matches_per_s": 1.0 / lat,
+                  "note": "batch of 1 through ndtpso_align_batch: host staging + H2D + K0/K1/K2 on a 16-CTA cluster + D2H"}
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         value = world * B * args.steps / (total_ms * 1e-3)
@@ -334,11 +363,12 @@ def run_gpu_arm(args):
                     "one_call_sync": world * B * args.steps / e2e_sync_s},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "pso_kernel", "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "pso_sliced_kernel", "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": measured_traffic(B), "peak_source": peak_src,
                          "kernel_ms": {"compact_map": float(kt[0]), "rng_fill": float(kt[1]), "pso": float(kt[2])},
                          "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                                   "note": "algorithmic flops (31/point-eval); peak = DFMA probe on this GPU; this is the bound that binds"}},
+            "single_match": single,
             "rounds_per_match": float(stats[:, 0].mean()), "pose0": [float(v) for v in pose[0]],
         }
         if not args.no_cpu:

@@ -644,7 +644,8 @@ int launch_sliced(ndtpso_batch* bt) {
                                                                                         : launch_sliced_cfg<1, 4, 1, 640, 1>(bt, nw, 1, smem);
     case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 1, 640, 1>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<2, 2, 1, 640, 1>(bt, nw, 1, smem)
                                                                                         : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem);
-    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem) : launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem);
+    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem)
+                                                                                        : launch_sliced_cfg<3, 4, 1, 384, 2>(bt, nw, 1, smem);
     case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem);
     case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem);
     default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem);

@@ -50,7 +50,7 @@ int run_var(int var, ndtpso_batch* bt, int nw, int grid, int ncand, int reps, do
 }
 }  // namespace
 
-// cfg: 0=(2,4,640,1) 1=(3,2,384,1) 2=(4,2,320,2) 3=(6,2,256,2) 4=(4,2,288,3) 5=(6,2,192,3) 6=(6,2,192,4) 7=(6,1,192,3) 8=(3,2,384,2)
+// cfg: 0=(2,2,576,2) 1=(2,1,576,2) 2=(4,2,320,2) 3=(3,4,384,2) 4=(4,2,288,3) 5=(3,2,384,3) 6=(2,4,576,2) 7=(6,1,192,3) 8=(3,2,384,2)
 extern "C" int ndtpso_bench_score(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int cfg, int var, int grid, int ncand, int reps,
                                   double* out_ms, int* out_info /* [4]: npt, warps, regs, ctas/SM */) {
   ndtpso_pso_config conf;
@@ -59,18 +59,18 @@ extern "C" int ndtpso_bench_score(ndtpso_ctx* ctx, int32_t n, const ndtpso_probl
   int rc = ndtpso_batch_create(ctx, n, problems, &conf, &bt);
   if (rc) return rc;
   rc = launch_compact(bt);
-  static const int npts[] = {2, 3, 4, 6, 4, 6, 6, 6, 3};
+  static const int npts[] = {2, 2, 4, 3, 4, 3, 2, 6, 3};
   const int npt = npts[cfg];
   const int nw = std::max(4, (bt->max_pts + 32 * npt - 1) / (32 * npt));
   int regs = 0, occ = 0;
   if (rc == NDTPSO_OK) switch (cfg) {
-      case 0: rc = run_var<2, 4, 640, 1>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
-      case 1: rc = run_var<3, 2, 384, 1>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
+      case 0: rc = run_var<2, 2, 576, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
+      case 1: rc = run_var<2, 1, 576, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
       case 2: rc = run_var<4, 2, 320, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
-      case 3: rc = run_var<6, 2, 256, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
+      case 3: rc = run_var<3, 4, 384, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
       case 4: rc = run_var<4, 2, 288, 3>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
-      case 5: rc = run_var<6, 2, 192, 3>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
-      case 6: rc = run_var<6, 2, 192, 4>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
+      case 5: rc = run_var<3, 2, 384, 3>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
+      case 6: rc = run_var<2, 4, 576, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
       case 7: rc = run_var<6, 1, 192, 3>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
       default: rc = run_var<3, 2, 384, 2>(var, bt, nw, grid, ncand, reps, out_ms, &regs, &occ); break;
     }

@@ -18,10 +18,10 @@ if __name__ == "__main__":
     L.ndtpso_last_error.argtypes = [C.c_void_p]; L.ndtpso_last_error.restype = C.c_char_p
     h = C.c_void_p(); assert L.ndtpso_ctx_create(0, C.byref(h)) == 0
     ps = capi.ProblemSet(workload.cfg2_batch(8))
-    names = ["(2,4,640,1)", "(3,2,384,1)", "(4,2,320,2)", "(6,2,256,2)", "(4,2,288,3)", "(6,2,192,3)", "(6,2,192,4)", "(6,1,192,3)", "(3,2,384,2)"]
+    names = ["(2,2,576,2)", "(2,1,576,2)", "(4,2,320,2)", "(3,4,384,2)", "(4,2,288,3)", "(3,2,384,3)", "(2,4,576,2)", "(6,1,192,3)", "(3,2,384,2)"]
     ncand, reps = 72, 40
     for cfg in range(9):
-        for var in range(4):
+        for var in (0,):
             ms = C.c_double(); info = (C.c_int * 4)()
             for grid_mult in (0,):
                 rc = L.ndtpso_bench_score(h, ps.n, ps.array, cfg, var, 148 * 8, ncand, reps, C.byref(ms), info)

@@ -10,7 +10,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libndtpso_b200.so")
 SOURCES = [os.path.join(CSRC, "ndtpso_capi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "ndtpso_kernels.cuh"), os.path.join(PKG, "..", "include", "ndtpso_b200.h")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("ndtpso_kernels.cuh", "ndtpso_pso_sliced.cuh", "ndtpso_dframes.cuh", "ndtpso_dframes_host.inc", "fast_exp.h")]
+DEPS += [os.path.join(PKG, "..", "include", f) for f in ("ndtpso_b200.h", "ndtpso_dframes.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

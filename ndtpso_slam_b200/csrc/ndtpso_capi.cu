@@ -21,6 +21,8 @@
 
 #include "ndtpso_kernels.cuh"
 #include "ndtpso_pso_sliced.cuh"
+#include "ndtpso_dframes.cuh"
+#include "../../include/ndtpso_dframes.h"
 
 using namespace ndtpso;
 
@@ -70,6 +72,7 @@ struct ndtpso_batch {
   DevMap* d_maps = nullptr;
   double* d_out = nullptr;
   int* d_stats = nullptr;
+  uint32_t* d_rng_state = nullptr;  // per-problem persistent rand() streams (device-resident frames), or nullptr
   int need_dyn_smem = 0;  // points + records + grid of the largest problem
   int max_pts = 0;        // largest scan
   int max_table_smem = 0; // records + grid of the largest table
@@ -652,6 +655,25 @@ int launch_sliced(ndtpso_batch* bt) {
   }
 }
 
+// K2: the point-sliced kernel when the batch qualifies, else the generic warp-per-particle kernel
+// (any scan length, any table size)
+int launch_pso_any(ndtpso_batch* bt) {
+  ndtpso_ctx* ctx = bt->ctx;
+  int rc = ctx->opt_kernel == 1 ? 1 : launch_sliced(bt);
+  if (rc == 1) {
+    if (ctx->opt_kernel == 2) return fail(ctx, NDTPSO_ERR_LIMIT, "batch does not qualify for the point-sliced kernel");
+    const int fixed = pso_fixed_smem_bytes(bt->prm.P);
+    const int smem = pick_smem(ctx, fixed, bt->need_dyn_smem);
+    switch (pick_warps(ctx)) {
+      case 4: rc = launch_pso<4>(bt, smem); break;
+      case 16: rc = launch_pso<16>(bt, smem); break;
+      case 32: rc = launch_pso<32>(bt, smem); break;
+      default: rc = launch_pso<8>(bt, smem); break;
+    }
+  }
+  return rc;
+}
+
 int launch_compact(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   if (bt->n_maps == 0) return NDTPSO_OK;
@@ -830,23 +852,12 @@ int ndtpso_batch_solve(ndtpso_batch* bt) {
   if (rc) return rc;
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[1], ctx->stream));
   if (bt->any_device_rng) {
-    rng_fill_kernel<<<(bt->n + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, ctx->stream>>>(bt->d_probs, bt->n, bt->prm.n_draws);
+    rng_fill_kernel<<<(bt->n + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, ctx->stream>>>(bt->d_probs, bt->n, bt->prm.n_draws, bt->d_rng_state);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
   }
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[2], ctx->stream));
-  rc = ctx->opt_kernel == 1 ? 1 : launch_sliced(bt);
-  if (rc == 1) {  // generic warp-per-particle kernel: any scan length, any table size
-    if (ctx->opt_kernel == 2) return fail(ctx, NDTPSO_ERR_LIMIT, "batch does not qualify for the point-sliced kernel");
-    const int fixed = pso_fixed_smem_bytes(bt->prm.P);
-    const int smem = pick_smem(ctx, fixed, bt->need_dyn_smem);
-    switch (pick_warps(ctx)) {
-      case 4: rc = launch_pso<4>(bt, smem); break;
-      case 16: rc = launch_pso<16>(bt, smem); break;
-      case 32: rc = launch_pso<32>(bt, smem); break;
-      default: rc = launch_pso<8>(bt, smem); break;
-    }
-  }
+  rc = launch_pso_any(bt);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[3], ctx->stream));
   bt->solved = true;
@@ -1067,3 +1078,5 @@ int ndtpso_measure_fp64_peak(ndtpso_ctx* ctx, double* out_tflops) {
 }
 
 }  // extern "C"
+
+#include "ndtpso_dframes_host.inc"

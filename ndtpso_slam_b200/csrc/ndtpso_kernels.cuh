@@ -210,8 +210,15 @@ __global__ void __launch_bounds__(K0_THREADS) compact_map_kernel(const DevMap* _
 // ------------------------------------------------------------------------------------------
 constexpr int K1_WARPS = 4;
 constexpr int K1_RING = 512;  // >= 341 + 32, power of two
+// Persistent generator state of one stream (NDTPSO_RNG_CONTINUE: the reference never seeds, so a
+// process' rand() stream continues from one align() to the next): the ring, where it stands, and
+// how many generated values have not been handed out yet.
+enum { K1_ST_NMOD = K1_RING, K1_ST_AHEAD, K1_ST_INIT, K1_ST_PAD, K1_STATE_WORDS };
 
-__global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProblem* __restrict__ probs, int n_problems, int n_draws) {
+// `state` == nullptr: every problem's stream is that of srand(probs[b].seed).
+// `state` != nullptr: problem b continues the stream kept in state[b] (seeded with probs[b].seed on first use).
+__global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProblem* __restrict__ probs, int n_problems, int n_draws,
+                                                                 uint32_t* __restrict__ state) {
   __shared__ uint32_t ring_all[K1_WARPS][K1_RING];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * K1_WARPS + warp;
@@ -219,32 +226,44 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
   if (probs[b].rnd_from_host) return;
   uint32_t* z = ring_all[warp];
   int* out = const_cast<int*>(probs[b].rnd);
+  uint32_t* st = state ? state + (size_t)b * K1_STATE_WORDS : nullptr;
 
-  if (lane == 0) {
-    uint32_t seed = probs[b].seed;
-    if (seed == 0) seed = 1;
-    // state[i], i = 0..30 ; z index of state[i] is (i + 28) % 31
-    int word = static_cast<int>(seed);  // glibc keeps `word` in an int32_t: seeds >= 2^31 go negative
-    z[28] = seed;
-    for (int i = 1; i < 31; ++i) {
-      const long long hi = word / 127773, lo = word % 127773;
-      long long t = 16807 * lo - 2836 * hi;
-      if (t < 0) t += 2147483647;
-      word = static_cast<int>(t);
-      z[(i + 28) % 31] = static_cast<uint32_t>(word);
-    }
-  }
-  __syncwarp();
-  // z[31 .. 372]: three values per step (lag 3 is the shortest)
-  for (int n = 31; n < 373; n += 3) {
-    if (lane < 3 && n + lane < 373) z[n + lane] = z[n + lane - 31] + z[n + lane - 3];
+  int n_loc, ahead;  // next index to generate (ring coordinates, >= K1_RING); values generated but not handed out
+  if (st && st[K1_ST_INIT]) {
+    for (int i = lane; i < K1_RING; i += 32) z[i] = st[i];
+    n_loc = K1_RING + static_cast<int>(st[K1_ST_NMOD]);
+    ahead = static_cast<int>(st[K1_ST_AHEAD]);
     __syncwarp();
+  } else {
+    if (lane == 0) {
+      uint32_t seed = probs[b].seed;
+      if (seed == 0) seed = 1;
+      // state[i], i = 0..30 ; z index of state[i] is (i + 28) % 31
+      int word = static_cast<int>(seed);  // glibc keeps `word` in an int32_t: seeds >= 2^31 go negative
+      z[28] = seed;
+      for (int i = 1; i < 31; ++i) {
+        const long long hi = word / 127773, lo = word % 127773;
+        long long t = 16807 * lo - 2836 * hi;
+        if (t < 0) t += 2147483647;
+        word = static_cast<int>(t);
+        z[(i + 28) % 31] = static_cast<uint32_t>(word);
+      }
+    }
+    __syncwarp();
+    // z[31 .. 372]: three values per step (lag 3 is the shortest)
+    for (int n = 31; n < 373; n += 3) {
+      if (lane < 3 && n + lane < 373) z[n + lane] = z[n + lane - 31] + z[n + lane - 3];
+      __syncwarp();
+    }
+    n_loc = K1_RING + 373;  // rand k = z[341 + k] >> 1: the first 32 are already in the history
+    ahead = 32;
   }
-  // outputs that are already in the history: rand k = z[341 + k] >> 1, k = 0..31
-  if (lane < n_draws) out[lane] = static_cast<int>(z[341 + lane] >> 1);
-  // then 32 per step: n = 373 + 32 s + lane  <->  k = n - 341
-  for (int n0 = 373; n0 - 341 < n_draws; n0 += 32) {
-    const int n = n0 + lane;
+  // values that are already in the history
+  for (int j = lane; j < min(ahead, n_draws); j += 32) out[j] = static_cast<int>(z[(n_loc - ahead + j) & (K1_RING - 1)] >> 1);
+  // then 32 per step
+  int t0 = 0;
+  for (; ahead + t0 < n_draws; t0 += 32) {
+    const int n = n_loc + t0 + lane;
     uint32_t v = z[(n - 33) & (K1_RING - 1)] + z[(n - 341) & (K1_RING - 1)];
     v += 11u * (z[(n - 61) & (K1_RING - 1)] + z[(n - 313) & (K1_RING - 1)]);
     v += 55u * (z[(n - 89) & (K1_RING - 1)] + z[(n - 285) & (K1_RING - 1)]);
@@ -253,9 +272,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
     v += 462u * (z[(n - 173) & (K1_RING - 1)] + z[(n - 201) & (K1_RING - 1)]);
     __syncwarp();
     z[n & (K1_RING - 1)] = v;
-    const int k = n - 341;
-    if (k < n_draws) out[k] = static_cast<int>(v >> 1);
+    const int j = ahead + t0 + lane;
+    if (j < n_draws) out[j] = static_cast<int>(v >> 1);
     __syncwarp();
+  }
+  if (st) {
+    for (int i = lane; i < K1_RING; i += 32) st[i] = z[i];
+    if (lane == 0) {
+      st[K1_ST_NMOD] = static_cast<uint32_t>((n_loc + t0) & (K1_RING - 1));
+      st[K1_ST_AHEAD] = static_cast<uint32_t>(ahead + t0 - n_draws);
+      st[K1_ST_INIT] = 1u;
+    }
   }
 }
 

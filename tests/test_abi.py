@@ -84,3 +84,27 @@ def test_null_arguments_are_errors_not_crashes(lib):
     lib.ndtpso_ctx_destroy(None)
     lib.ndtpso_batch_destroy(None)
     assert lib.ndtpso_rand_draws(None) == 0
+
+
+def test_dframes_header_exports_and_layout(lib):
+    """include/ndtpso_dframes.h: every declared entry point is exported; the config struct mirrors the header."""
+    from ndtpso_slam_b200 import dframes
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ndtpso_dframes.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ndtpso_dframes_[a-z0-9_]+)\s*\(", src)))
+    assert len(declared) == 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ndtpso_dframes.h but not exported"
+    assert sorted(dframes.EXPORTS) == declared
+    assert C.sizeof(dframes.DFramesConfig) == 48
+    cfg = dframes.DFramesConfig()
+    dframes._lib().ndtpso_dframes_config_default(C.byref(cfg))
+    # NDTFrame's constructor defaults (ndtframe.h:39-40) and LASER_IGNORE_EPSILON (config.h:6)
+    assert (cfg.width_m, cfg.height_m, cfg.cell_side, cfg.max_beams) == (20, 20, 1.0, 1081)
+    assert abs(cfg.laser_ignore_epsilon - 0.1) < 1e-7
+    # null handles are errors, not crashes
+    L = dframes._lib()
+    assert L.ndtpso_dframes_create(None, None, None) == capi.ERR_ARG
+    assert L.ndtpso_dframes_update(None, None) == capi.ERR_ARG
+    assert L.ndtpso_dframes_align(None, None, None, 0, None, None, None) == capi.ERR_ARG
+    assert L.ndtpso_dframes_device_bytes(None) == 0
+    L.ndtpso_dframes_destroy(None)

@@ -201,6 +201,50 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def run_tracking(ctx, B, conf, steps):
+    """B robots, each tracked through the reference's per-scan callback (src/ndtpso_slam_node.cpp:177-244) with its map
+    resident in HBM (include/ndtpso_dframes.h).  Robot b replays trajectory b of the bench workload: its map is seeded with
+    the 5 map scans of synthetic.trajectory_problem(CFG2, b), then every timed step is one ndtpso_dframes_track_step call:
+    H2D of the step's ranges (4 bytes per beam), loadLaser, NDTFrame::build + table compaction, rand() stream, PSO,
+    NDTFrame::update, D2H of the poses.  Steps are sequentially dependent (the pose of scan k positions scan k in the map
+    that scan k+1 is matched against), so nothing is pipelined; wall clock around the K calls."""
+    from ndtpso_slam_b200 import dframes, synthetic as syn
+    cfg = syn.CFG2
+    s, S = cfg.sensor, cfg.map_size_m
+    room = syn.Room(S)
+    df = dframes.DeviceFrames(ctx, B, S, S, cfg.cell_side, s.beams, max_cells=1024)
+    sets = [syn.trajectory_problem(cfg, b) for b in range(B)]
+    for k in range(5):  # the map: 5 scans per robot merged at their known poses
+        df.load_laser(np.stack([ss.map_scans[k][1] for ss in sets]), s.angle_min, s.angle_increment, s.range_max)
+        df.update(np.array([ss.map_scans[k][0] for ss in sets]))
+    # the tracked scans: robot b moves on from its query pose, 2 cm and 1 mrad per scan
+    scans = []
+    for k in range(steps + 2):
+        scans.append(np.stack([syn.make_scan(room, s, (ss.true_pose[0] + 0.02 * k, ss.true_pose[1] + 0.005 * k, ss.true_pose[2] + 0.001 * k),
+                                             syn.NoiseLCG(777 + 131 * b + k)) for b, ss in enumerate(sets)]))
+    init = np.array([ss.guess for ss in sets])
+    df.track_step(scans[0], s.angle_min, s.angle_increment, s.range_max, initial_poses=init, conf=conf)  # first scan: no matching
+    df.track_step(scans[1], s.angle_min, s.angle_increment, s.range_max, initial_poses=None, conf=conf)   # warm-up
+    kt = []
+    t0 = time.perf_counter()
+    for k in range(steps):
+        pose, cost = df.track_step(scans[2 + k], s.angle_min, s.angle_increment, s.range_max, initial_poses=None, conf=conf)
+    wall = time.perf_counter() - t0
+    kt = df.kernel_times_ms()
+    true_last = np.array([(ss.true_pose[0] + 0.02 * (steps + 1), ss.true_pose[1] + 0.005 * (steps + 1), ss.true_pose[2] + 0.001 * (steps + 1))
+                          for ss in sets])
+    err = np.abs(pose - true_last)
+    info = df.info(0)
+    flags = int(np.bitwise_or.reduce(df.status()))
+    out = {"value": B * steps / wall, "unit": "scan-matches/s", "robots": B, "steps": steps, "ms_per_step": 1e3 * wall / steps,
+           "h2d_bytes_per_step": int(B * s.beams * 4), "d2h_bytes_per_step": int(B * 32), "kernel_ms_last_step": kt,
+           "device_bytes": df.device_bytes(), "cells_created_robot0": info["created"], "cells_built_robot0": info["built"], "status_bits": flags,
+           "median_abs_pose_error_vs_truth": [float(v) for v in np.median(err, axis=0)],
+           "api": "ndtpso_dframes_track_step: loadLaser + build + PSO 70x50 + update per call, maps resident in HBM"}
+    df.close()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -343,6 +387,11 @@ def run_gpu_arm(args):
         single = {"resident_ms": float(np.median(ks[args.warmup:])), "e2e_ms": 1e3 * lat, "e2e_matches_per_s": 1.0 / lat,
                   "note": "batch of 1 through ndtpso_align_batch: host staging + H2D + K0/K1/K2 on a 16-CTA cluster + D2H"}
 
+    # ---- the per-scan callback with the maps resident in HBM: loadLaser -> align -> update
+    tracking = None
+    if rank == 0 and not args.no_tracking:
+        tracking = run_tracking(ctx, B, conf, steps=max(4, min(args.steps, 12)))
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         value = world * B * args.steps / (total_ms * 1e-3)
@@ -369,6 +418,7 @@ def run_gpu_arm(args):
                          "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                                   "note": "algorithmic flops (31/point-eval); peak = DFMA probe on this GPU; this is the bound that binds"}},
             "single_match": single,
+            "tracking": tracking,
             "rounds_per_match": float(stats[:, 0].mean()), "pose0": [float(v) for v in pose[0]],
         }
         if not args.no_cpu:
@@ -389,6 +439,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-matches", type=int, default=4, help="CPU arm: matches per host worker per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-tracking", action="store_true", help="skip the device-resident tracking leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -34,7 +34,8 @@ namespace ndtpso {
 
 constexpr int kWindow = 100;        // NDT_WINDOW_SIZE           config.h:8
 constexpr int kMaxPerCell = 50;     // NDT_MAX_POINTS_PER_CELL   config.h:5
-constexpr int kDfThreads = 256;
+constexpr int kDfThreads = 512;
+constexpr int kDfBuildThreads = 512;
 
 enum { DF_CELL_POOL_FULL = 1, DF_WINDOW_TRUNCATED = 2, DF_INDEX_PAST_END = 4, DF_IRREGULAR_SIGMA = 8 };
 
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kDfThreads) frame_update_kernel(DevFrames F, c
 }
 
 // ---- build -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) frame_build_kernel(DevFrames F) {
+__global__ void __launch_bounds__(kDfBuildThreads) frame_build_kernel(DevFrames F) {
   const int b = blockIdx.x;
   const int n_created = F.n_created[b];
   const size_t pool0 = (size_t)b * F.max_cells;

@@ -246,6 +246,18 @@ def run_tracking(ctx, B, conf, steps):
 
 
 def run_gpu_arm(args):
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _run_gpu_arm(args, real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+
+
+def _run_gpu_arm(args, real_stdout):
     import torch
     import torch.distributed as dist
 
@@ -299,10 +311,45 @@ def run_gpu_arm(args):
             __cuda_array_interface__ = {"shape": (B * 4,), "typestr": "<f8", "data": (res_ptr, False), "version": 3}
         res_t = torch.as_tensor(_Ext(), device="cuda")
 
+    # The one exchange of the path: every rank ends up with all solved poses.  Fused form: the PSO kernel's epilogue
+    # stores each result into every rank's gathered buffer over NVLink (CUDA IPC) and ndtpso_exchange_wait polls the
+    # arrival flags — no collective per step.  NCCL's all-gather is the reference implementation: used to verify the
+    # fused form once, and as the per-step exchange if CUDA IPC is unavailable (--exchange nccl forces it).
+    ex, exchange_kind = None, "none"
+    if world > 1:
+        exchange_kind = "NCCL all-gather of [B][4] fp64 poses per step"
+        if args.exchange == "fused":
+            try:
+                ex = sharding.make_exchange(ctx, B, world, rank, device="cuda")
+                bt.attach_exchange(ex)
+                exchange_kind = ("peer stores of the [B][4] fp64 poses from the PSO kernel's epilogue into every rank's gathered buffer "
+                                 "(NVLink, CUDA IPC) + arrival-flag wait kernel; verified against an NCCL all-gather")
+            except Exception as e:  # noqa: BLE001
+                print(f"rank {rank}: fused exchange unavailable ({e}); using NCCL", file=sys.stderr)
+                ex = None
+        ok = torch.tensor([1 if ex is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ex is not None and int(ok.item()) == 0:
+            bt.attach_exchange(None)
+            ex = None
+            exchange_kind = "NCCL all-gather of [B][4] fp64 poses per step"
+
     def resident_step():
         bt.solve()
-        if world > 1:  # the one exchange of the path: every rank gets all solved poses
+        if ex is not None:
+            ex.wait()
+        elif world > 1:
             sharding.gather_results(res_t.view(B, 4), world * B, world, rank)
+
+    if ex is not None:  # once: the fused exchange delivers exactly what the collective delivers
+        resident_step()
+        class _ExG:
+            __cuda_array_interface__ = {"shape": (world * B * 4,), "typestr": "<f8", "data": (ex.device_results_ptr(), False), "version": 3}
+        torch.cuda.synchronize()
+        fused = torch.as_tensor(_ExG(), device="cuda").view(world * B, 4).clone()
+        ref_rows = sharding.gather_results(res_t.view(B, 4), world * B, world, rank)
+        torch.cuda.synchronize()
+        assert torch.equal(fused, ref_rows), "fused exchange and NCCL all-gather disagree"
 
     for _ in range(args.warmup):
         l2_flush.fill_(1)
@@ -366,6 +413,8 @@ def run_gpu_arm(args):
     assert np.array_equal(ep, pose), "e2e and resident paths disagree"
 
     fp64_peak = ctx.fp64_peak_tflops()
+    if ex is not None:
+        bt.attach_exchange(None)
     bt.close()
 
     # ---- configs[1] read literally: ONE scan-match at a time (thread-block-cluster form of the kernel)
@@ -406,7 +455,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"cfg2 shape (configs[1]; batched as configs[2]): {B} independent 1081-beam scan-matches per GPU vs "
                                    "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations",
                        "batch_per_gpu": B, "particles": P, "iterations": I, "l2": "flushed between timed iterations (256 MiB write)",
-                       "collective": "NCCL all-gather of [B][4] fp64 poses per step" if world > 1 else "none"},
+                       "collective": exchange_kind},
             "e2e": {"value": e2e, "unit": "scan-matches/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "api": "ndtpso_align_submit/collect, 2 batches in flight",
                     "one_call_sync": world * B * args.steps / e2e_sync_s},
@@ -423,8 +472,12 @@ def run_gpu_arm(args):
         }
         if not args.no_cpu:
             line["cpu_baseline"], _ = cpu_reference_rate(args.ref_matches)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
+        dist.barrier()
+        if ex is not None:
+            ex.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0
@@ -440,6 +493,7 @@ def main():
     ap.add_argument("--ref-matches", type=int, default=4, help="CPU arm: matches per host worker per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tracking", action="store_true", help="skip the device-resident tracking leg")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N > 1: how the solved poses reach every rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

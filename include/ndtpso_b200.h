@@ -118,7 +118,8 @@ enum {
   NDTPSO_OPT_KERNEL = 4,        /* 0 = auto, 1 = warp-per-particle (generic), 2 = point-sliced */
   NDTPSO_OPT_POINTS_PER_THREAD = 5, /* point-sliced kernel: scan points held per thread; 0 = auto */
   NDTPSO_OPT_CANDIDATE_BATCH = 6,  /* point-sliced kernel: candidates scored together (1, 2, 4); 0 = auto */
-  NDTPSO_OPT_PIPELINE_CHUNKS = 7   /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4, default 1) */
+  NDTPSO_OPT_PIPELINE_CHUNKS = 7,  /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4, default 1) */
+  NDTPSO_OPT_EXCHANGE_TIMEOUT_MS = 8 /* ndtpso_exchange_wait: give up after this long (default 10000) */
 };
 int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value);
 
@@ -166,6 +167,37 @@ int64_t ndtpso_ctx_launch_count(const ndtpso_ctx* ctx);
  * read of this context (what bench.py reports as h2d/d2h bytes per step) */
 int ndtpso_ctx_last_transfer_bytes(const ndtpso_ctx* ctx, int64_t* h2d, int64_t* d2h);
 int ndtpso_ctx_synchronize(ndtpso_ctx* ctx);
+
+/* ---- multi-GPU: the solved poses of every rank on every rank, without a collective call ------ */
+/* The path shards over independent problems, one shard per GPU (one process per GPU); its only exchange
+ * is the gather of the solved poses at the end.  An exchange replaces that collective by peer stores
+ * fused into the PSO kernel's epilogue: the CTA that solved a problem writes its (x, y, theta, cost)
+ * into the gathered buffer of every rank over NVLink (CUDA IPC mappings), and the last CTA of a launch
+ * raises its rank's arrival flag everywhere.  ndtpso_exchange_wait then enqueues a small kernel that
+ * returns once all ranks' flags of the current epoch have arrived (bounded spin, never a hang).
+ * Buffers are double-buffered by epoch, so a rank may be one solve ahead of its peers. */
+typedef struct ndtpso_exchange ndtpso_exchange;
+#define NDTPSO_IPC_HANDLE_BYTES 64
+#define NDTPSO_MAX_RANKS 8
+/* Allocates this rank's gathered buffer ([2][world * n_per_rank][4] fp64) and writes the 64-byte handle
+ * the other ranks need to map it. */
+int ndtpso_exchange_create(ndtpso_ctx* ctx, int32_t world, int32_t rank, int32_t n_per_rank, ndtpso_exchange** out,
+                           void* out_ipc_handle /* [NDTPSO_IPC_HANDLE_BYTES] */);
+/* all_handles: [world][NDTPSO_IPC_HANDLE_BYTES], every rank's handle in rank order (gathered by the
+ * caller, e.g. with torch.distributed.all_gather).  Maps the peers' buffers. */
+int ndtpso_exchange_connect(ndtpso_exchange* ex, const void* all_handles);
+/* The same for ranks that live in ONE process (one context per GPU): peers[r] = rank r's exchange. */
+int ndtpso_exchange_connect_local(ndtpso_exchange* ex, ndtpso_exchange* const* peers);
+/* Every later ndtpso_batch_solve of `batch` (n == n_per_rank problems) also publishes its results through `ex`;
+ * ex = NULL detaches. */
+int ndtpso_batch_attach_exchange(ndtpso_batch* batch, ndtpso_exchange* ex);
+/* Enqueue the wait for the epoch of the most recent solve on the context's stream (asynchronous). */
+int ndtpso_exchange_wait(ndtpso_exchange* ex);
+/* device pointer to the gathered results of that epoch, [world * n_per_rank][4] fp64, valid after the wait */
+void* ndtpso_exchange_device_results(ndtpso_exchange* ex);
+/* wait + D2H + synchronise: out_pose [world * n_per_rank][3], out_cost [world * n_per_rank]; either may be NULL */
+int ndtpso_exchange_results(ndtpso_exchange* ex, double* out_pose, double* out_cost);
+void ndtpso_exchange_destroy(ndtpso_exchange* ex);
 
 /* ---- device self-measurement (roofline denominators MEASURED_PEAKS.json lacks) --- */
 /* Sustained fp64 FMA throughput of this GPU in TFLOP/s (2 flop per DFMA). */

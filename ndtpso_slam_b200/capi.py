@@ -15,6 +15,7 @@ from . import build as _build
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_LIMIT = 0, -1, -2, -3, -4, -5
 OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREAD, OPT_CANDIDATE_BATCH, OPT_PIPELINE_CHUNKS = 1, 2, 3, 4, 5, 6, 7
+OPT_EXCHANGE_TIMEOUT_MS = 8
 KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 
 #: every symbol include/ndtpso_b200.h declares
@@ -23,7 +24,10 @@ EXPORTS = [
     "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch", "ndtpso_align_submit", "ndtpso_align_collect",
     "ndtpso_cost_batch", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
     "ndtpso_batch_stats", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
+    "ndtpso_exchange_create", "ndtpso_exchange_connect", "ndtpso_exchange_connect_local", "ndtpso_batch_attach_exchange", "ndtpso_exchange_wait",
+    "ndtpso_exchange_device_results", "ndtpso_exchange_results", "ndtpso_exchange_destroy",
 ]
+IPC_HANDLE_BYTES, MAX_RANKS = 64, 8
 
 
 class PsoConfig(C.Structure):
@@ -98,6 +102,16 @@ def load_library(build_if_missing: bool = True):
     L.ndtpso_ctx_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ndtpso_ctx_synchronize.argtypes = [C.c_void_p]
     L.ndtpso_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.ndtpso_exchange_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
+    L.ndtpso_exchange_connect.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndtpso_exchange_connect_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.ndtpso_batch_attach_exchange.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndtpso_exchange_wait.argtypes = [C.c_void_p]
+    L.ndtpso_exchange_device_results.argtypes = [C.c_void_p]
+    L.ndtpso_exchange_device_results.restype = C.c_void_p
+    L.ndtpso_exchange_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ndtpso_exchange_destroy.argtypes = [C.c_void_p]
+    L.ndtpso_exchange_destroy.restype = None
     _lib = L
     return L
 
@@ -159,6 +173,48 @@ class ProblemSet:
         return arr
 
 
+class Exchange:
+    """Gathered results of all ranks, filled by peer stores from the PSO kernel's epilogue (ndtpso_exchange_*)."""
+
+    def __init__(self, ctx: "Context", world: int, rank: int, n_per_rank: int):
+        self.ctx, self.world, self.rank, self.n = ctx, int(world), int(rank), int(n_per_rank)
+        self.h = C.c_void_p()
+        self.handle = np.zeros(IPC_HANDLE_BYTES, dtype=np.uint8)
+        ctx._check(ctx.lib.ndtpso_exchange_create(ctx.h, self.world, self.rank, self.n, C.byref(self.h), _ptr(self.handle)))
+
+    def connect(self, all_handles):
+        """all_handles: uint8 [world, 64], every rank's `handle` in rank order."""
+        a = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(self.world, IPC_HANDLE_BYTES)
+        self.ctx._check(self.ctx.lib.ndtpso_exchange_connect(self.h, _ptr(a)))
+
+    def connect_local(self, peers):
+        arr = (C.c_void_p * self.world)(*[p.h for p in peers])
+        self.ctx._check(self.ctx.lib.ndtpso_exchange_connect_local(self.h, arr))
+
+    def wait(self):
+        self.ctx._check(self.ctx.lib.ndtpso_exchange_wait(self.h))
+
+    def device_results_ptr(self) -> int:
+        return int(self.ctx.lib.ndtpso_exchange_device_results(self.h) or 0)
+
+    def results(self):
+        pose = np.empty((self.world * self.n, 3), dtype=np.float64)
+        cost = np.empty(self.world * self.n, dtype=np.float64)
+        self.ctx._check(self.ctx.lib.ndtpso_exchange_results(self.h, _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ndtpso_exchange_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Batch:
     """A batch resident in HBM (ndtpso_batch_*)."""
 
@@ -170,6 +226,9 @@ class Batch:
 
     def solve(self):
         self.ctx._check(self.ctx.lib.ndtpso_batch_solve(self.h))
+
+    def attach_exchange(self, ex):
+        self.ctx._check(self.ctx.lib.ndtpso_batch_attach_exchange(self.h, ex.h if ex is not None else None))
 
     def device_results_ptr(self) -> int:
         return int(self.ctx.lib.ndtpso_batch_device_results(self.h) or 0)

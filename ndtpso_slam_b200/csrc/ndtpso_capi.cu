@@ -55,9 +55,23 @@ struct ndtpso_ctx {
   int64_t launches = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the most recent upload / results call
   int sm_count = 0;
+  int clock_khz = 2000000;
+  int64_t opt_exchange_timeout_ms = 10000;  // bounded wait for the peers' results
   int max_smem_optin = 0;
   std::vector<PoolBuf> dev_pool, pin_pool;
   int smem_attr_set[33] = {0};
+};
+
+struct ndtpso_exchange {
+  ndtpso_ctx* ctx = nullptr;
+  int world = 1, rank = 0, n_per_rank = 0;
+  unsigned char* base = nullptr;  // [2][world*n][4] fp64 | flags[world] u32 | done u32 | err i32
+  size_t half_bytes = 0, o_flags = 0, o_done = 0, o_err = 0, bytes = 0;
+  unsigned char* peer_base[NDTPSO_MAX_RANKS] = {};
+  bool opened[NDTPSO_MAX_RANKS] = {};
+  bool connected = false;
+  unsigned epoch = 0;
+  double* pin = nullptr;  // [world*n][4] read-back staging
 };
 
 struct ndtpso_batch {
@@ -73,6 +87,7 @@ struct ndtpso_batch {
   double* d_out = nullptr;
   int* d_stats = nullptr;
   uint32_t* d_rng_state = nullptr;  // per-problem persistent rand() streams (device-resident frames), or nullptr
+  ndtpso_exchange* ex = nullptr;    // results are also published to every rank's gathered buffer (multi-GPU)
   int need_dyn_smem = 0;  // points + records + grid of the largest problem
   int max_pts = 0;        // largest scan
   int max_table_smem = 0; // records + grid of the largest table
@@ -655,6 +670,27 @@ int launch_sliced(ndtpso_batch* bt) {
   }
 }
 
+// Points the next PSO launch of `bt` at the gathered buffers of all ranks (next epoch), or switches publishing off.
+void exchange_arm(ndtpso_batch* bt) {
+  PeerExchange& px = bt->prm.ex;
+  ndtpso_exchange* ex = bt->ex;
+  if (!ex || !ex->connected) {
+    px.world = 0;
+    return;
+  }
+  ++ex->epoch;
+  const size_t half = (ex->epoch & 1u) * ex->half_bytes;
+  for (int r = 0; r < ex->world; ++r) {
+    px.out[r] = reinterpret_cast<double*>(ex->peer_base[r] + half);
+    px.flag[r] = reinterpret_cast<unsigned*>(ex->peer_base[r] + ex->o_flags);
+  }
+  px.done = reinterpret_cast<unsigned*>(ex->base + ex->o_done);
+  px.world = ex->world;
+  px.my_rank = ex->rank;
+  px.offset = ex->rank * ex->n_per_rank;
+  px.epoch = ex->epoch;
+}
+
 // K2: the point-sliced kernel when the batch qualifies, else the generic warp-per-particle kernel
 // (any scan length, any table size)
 int launch_pso_any(ndtpso_batch* bt) {
@@ -738,6 +774,7 @@ int ndtpso_ctx_create(int device, ndtpso_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   ctx->sm_count = prop.multiProcessorCount;
+  if (prop.clockRate > 0) ctx->clock_khz = prop.clockRate;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   *out = ctx;
   return NDTPSO_OK;
@@ -786,6 +823,10 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
     case NDTPSO_OPT_POINTS_PER_THREAD:
       if (value < 0 || value > kSlicedMaxNPT) return fail(ctx, NDTPSO_ERR_ARG, "points per thread out of range");
       ctx->opt_npt = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_EXCHANGE_TIMEOUT_MS:
+      if (value < 1 || value > 600000) return fail(ctx, NDTPSO_ERR_ARG, "exchange timeout must be in 1..600000 ms");
+      ctx->opt_exchange_timeout_ms = value;
       return NDTPSO_OK;
     case NDTPSO_OPT_SMEM_BYTES:
       if (value < 0 || value > ctx->max_smem_optin) return fail(ctx, NDTPSO_ERR_ARG, "shared memory bytes out of range");
@@ -857,6 +898,7 @@ int ndtpso_batch_solve(ndtpso_batch* bt) {
     ctx->launches++;
   }
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[2], ctx->stream));
+  exchange_arm(bt);
   rc = launch_pso_any(bt);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[3], ctx->stream));
@@ -1045,6 +1087,140 @@ int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
   return cleanup(NDTPSO_OK);
+}
+
+int ndtpso_exchange_create(ndtpso_ctx* ctx, int32_t world, int32_t rank, int32_t n_per_rank, ndtpso_exchange** out, void* out_ipc_handle) {
+  if (!ctx || !out || world < 1 || world > NDTPSO_MAX_RANKS || rank < 0 || rank >= world || n_per_rank < 1)
+    return fail(ctx, NDTPSO_ERR_ARG, "exchange_create: bad argument");
+  *out = nullptr;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ndtpso_exchange* ex = new (std::nothrow) ndtpso_exchange();
+  if (!ex) return fail(ctx, NDTPSO_ERR_NOMEM, "exchange_create: host allocation failed");
+  ex->ctx = ctx;
+  ex->world = world;
+  ex->rank = rank;
+  ex->n_per_rank = n_per_rank;
+  ex->half_bytes = align_up(sizeof(double) * 4 * (size_t)world * n_per_rank);
+  ex->o_flags = 2 * ex->half_bytes;
+  ex->o_done = ex->o_flags + align_up(sizeof(unsigned) * NDTPSO_MAX_RANKS);
+  ex->o_err = ex->o_done + kAlign;
+  ex->bytes = ex->o_err + kAlign;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->base), ex->bytes);  // its own allocation: the IPC handle maps exactly this
+  if (e == cudaSuccess) e = cudaMemset(ex->base, 0, ex->bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ex->pin), sizeof(double) * 4 * (size_t)world * n_per_rank);
+  if (e == cudaSuccess && out_ipc_handle) {
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == NDTPSO_IPC_HANDLE_BYTES, "IPC handle size");
+    e = cudaIpcGetMemHandle(&h, ex->base);
+    if (e == cudaSuccess) memcpy(out_ipc_handle, &h, sizeof h);
+  }
+  if (e != cudaSuccess) {
+    const std::string msg = cudaGetErrorString(e);
+    cudaGetLastError();
+    ndtpso_exchange_destroy(ex);
+    return fail(ctx, NDTPSO_ERR_CUDA, "exchange_create: " + msg);
+  }
+  ex->peer_base[rank] = ex->base;
+  ex->connected = (world == 1);
+  *out = ex;
+  return NDTPSO_OK;
+}
+
+int ndtpso_exchange_connect(ndtpso_exchange* ex, const void* all_handles) {
+  if (!ex || !all_handles) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = ex->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < ex->world; ++r) {
+    if (r == ex->rank || ex->opened[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const unsigned char*>(all_handles) + (size_t)r * NDTPSO_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ex->peer_base[r] = static_cast<unsigned char*>(p);
+    ex->opened[r] = true;
+  }
+  ex->connected = true;
+  return NDTPSO_OK;
+}
+
+int ndtpso_exchange_connect_local(ndtpso_exchange* ex, ndtpso_exchange* const* peers) {
+  if (!ex || !peers) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = ex->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < ex->world; ++r) {
+    if (r == ex->rank) continue;
+    if (!peers[r] || peers[r]->world != ex->world || peers[r]->n_per_rank != ex->n_per_rank || peers[r]->rank != r)
+      return fail(ctx, NDTPSO_ERR_ARG, "exchange_connect_local: peers do not match");
+    const int pd = peers[r]->ctx->device;
+    if (pd != ctx->device) {
+      int can = 0;
+      CUDA_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, pd));
+      if (!can) return fail(ctx, NDTPSO_ERR_CUDA, "exchange_connect_local: no peer access between the devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    ex->peer_base[r] = peers[r]->base;
+  }
+  ex->connected = true;
+  return NDTPSO_OK;
+}
+
+int ndtpso_batch_attach_exchange(ndtpso_batch* bt, ndtpso_exchange* ex) {
+  if (!bt) return NDTPSO_ERR_ARG;
+  if (ex && (ex->ctx != bt->ctx || ex->n_per_rank != bt->n || !ex->connected))
+    return fail(bt->ctx, NDTPSO_ERR_ARG, "batch_attach_exchange: exchange not connected, or of another context / batch size");
+  bt->ex = ex;
+  return NDTPSO_OK;
+}
+
+int ndtpso_exchange_wait(ndtpso_exchange* ex) {
+  if (!ex || !ex->connected) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = ex->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long timeout_cycles = (long long)ctx->opt_exchange_timeout_ms * ctx->clock_khz;  // a peer that never arrives is an error, not a hang
+  exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned*>(ex->base + ex->o_flags), ex->world, ex->epoch,
+                                                   timeout_cycles, reinterpret_cast<int*>(ex->base + ex->o_err));
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return NDTPSO_OK;
+}
+
+void* ndtpso_exchange_device_results(ndtpso_exchange* ex) { return ex ? ex->base + (ex->epoch & 1u) * ex->half_bytes : nullptr; }
+
+int ndtpso_exchange_results(ndtpso_exchange* ex, double* out_pose, double* out_cost) {
+  if (!ex) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = ex->ctx;
+  int rc = ndtpso_exchange_wait(ex);
+  if (rc) return rc;
+  const size_t rows = (size_t)ex->world * ex->n_per_rank;
+  int err = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ex->pin, ndtpso_exchange_device_results(ex), sizeof(double) * 4 * rows, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(&err, ex->base + ex->o_err, sizeof err, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (err) return fail(ctx, NDTPSO_ERR_CUDA, "exchange: rank " + std::to_string(err - 1) + " did not arrive within the time limit");
+  for (size_t i = 0; i < rows; ++i) {
+    if (out_pose) {
+      out_pose[3 * i] = ex->pin[4 * i];
+      out_pose[3 * i + 1] = ex->pin[4 * i + 1];
+      out_pose[3 * i + 2] = ex->pin[4 * i + 2];
+    }
+    if (out_cost) out_cost[i] = ex->pin[4 * i + 3];
+  }
+  return NDTPSO_OK;
+}
+
+void ndtpso_exchange_destroy(ndtpso_exchange* ex) {
+  if (!ex) return;
+  if (ex->ctx) {
+    cudaSetDevice(ex->ctx->device);
+    cudaStreamSynchronize(ex->ctx->stream);
+  }
+  for (int r = 0; r < NDTPSO_MAX_RANKS; ++r)
+    if (ex->opened[r]) cudaIpcCloseMemHandle(ex->peer_base[r]);
+  if (ex->base) cudaFree(ex->base);
+  if (ex->pin) cudaFreeHost(ex->pin);
+  delete ex;
 }
 
 int ndtpso_measure_fp64_peak(ndtpso_ctx* ctx, double* out_tflops) {

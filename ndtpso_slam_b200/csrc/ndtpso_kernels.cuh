@@ -60,12 +60,62 @@ struct DevProblem {
   int rnd_from_host;    // 1: `rnd` was uploaded, K1 skips this problem
 };
 
+// Result exchange fused into the PSO kernels' epilogue (multi-GPU): instead of a collective after the
+// kernel, the CTA that solved problem b stores its 32-byte result straight into the gathered result
+// buffer of EVERY rank (its own and, over NVLink, its peers'), and the last CTA of the launch raises
+// this rank's arrival flag on every rank.  world == 0: off.
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+  double* out[kMaxPeers];     // rank r's gathered buffer [world * n_per_rank][4] (this epoch's half)
+  unsigned* flag[kMaxPeers];  // rank r's arrival flags [world]
+  unsigned* done;             // this rank's counter of finished problems
+  int world, my_rank, offset; // offset = first row of this rank's block
+  unsigned epoch;
+};
+
 struct PsoParams {
   int P, I;
   double w, c1, c2, wd;
   int n_draws;      // 3 + 3P + 6PI
   int smem_bytes;   // dynamic shared memory given to pso_kernel
+  PeerExchange ex;
 };
+
+// called by the one thread that wrote problem b's result `o` = {x, y, theta, cost}
+__device__ __forceinline__ void publish_result(const PeerExchange& ex, int b, int n_problems, const double* o) {
+  if (ex.world <= 0) return;
+  const double2 xy = make_double2(o[0], o[1]), tc = make_double2(o[2], o[3]);
+  for (int r = 0; r < ex.world; ++r) {
+    double2* dst = reinterpret_cast<double2*>(ex.out[r] + 4 * (size_t)(ex.offset + b));
+    dst[0] = xy;
+    dst[1] = tc;
+  }
+  __threadfence_system();  // the stores above are visible system-wide before this problem counts as done
+  const unsigned old = atomicAdd(ex.done, 1u);
+  if (old == static_cast<unsigned>(n_problems - 1)) {  // last problem of this launch
+    *ex.done = 0u;          // the next launch on this stream starts after this one has ended
+    __threadfence_system();  // orders every other CTA's stores (observed through the counter) before the flags
+    for (int r = 0; r < ex.world; ++r)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ex.flag[r] + ex.my_rank), "r"(ex.epoch) : "memory");
+  }
+}
+
+// Stream-ordered wait for every rank's flag to reach `epoch` (bounded: sets *err after `timeout_cycles`).
+__global__ void exchange_wait_kernel(const unsigned* flags, int world, unsigned epoch, long long timeout_cycles, int* err) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+    if (static_cast<int>(v - epoch) >= 0) break;
+    if (clock64() - t0 > timeout_cycles) {
+      atomicExch(err, 1 + r);
+      break;
+    }
+    __nanosleep(200);
+  }
+}
 
 __constant__ double c_exp_table[kExpTableSize] = {
 #include "exp_table.inc"
@@ -737,6 +787,7 @@ __global__ void __launch_bounds__(NW * 32) pso_kernel(const DevProblem* __restri
   } else {
     pso_body<CostOf<COST_SLOW>, NW>(CostOf<COST_SLOW>{st.slow}, pr, prm, sm, o, s);
   }
+  if (threadIdx.x == 0) publish_result(prm.ex, b, gridDim.x, o);
 }
 
 constexpr int kCostFixedSmem = 16 + kExpTableSize * (int)sizeof(double);

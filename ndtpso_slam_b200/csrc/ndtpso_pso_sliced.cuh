@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem
     sliced_body<NPT, JB, CL, true, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
   else
     sliced_body<NPT, JB, CL, false, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
+  if (threadIdx.x == 0 && tp.rank == 0) publish_result(prm.ex, b, gridDim.x / CL, o);  // the thread that wrote o
 }
 
 // Phase-B microbenchmark: every CTA stages problem blockIdx.x % n_problems and scores `ncand`

@@ -63,3 +63,23 @@ def solve_sharded(solve_fn, problems, world_size: int, rank: int, device=None, g
         rows = rows.to(device)
     allrows = gather_results(rows, len(problems), world_size, rank, group=group).cpu().numpy()
     return allrows[:, :3], allrows[:, 3]
+
+
+def make_exchange(ctx, n_per_rank: int, world_size: int, rank: int, group=None, device=None):
+    """The fused form of the exchange (include/ndtpso_b200.h, ndtpso_exchange_*): every rank allocates its gathered
+    result buffer, the 64-byte CUDA IPC handles are all-gathered once, and from then on the PSO kernel's epilogue stores
+    each result into every rank's buffer over NVLink — no collective per step.  Returns a connected capi.Exchange."""
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+
+    ex = capi.Exchange(ctx, world_size, rank, n_per_rank)
+    if world_size > 1:
+        mine = torch.from_numpy(ex.handle.copy())
+        if device is not None:
+            mine = mine.to(device)
+        allh = torch.empty((world_size, capi.IPC_HANDLE_BYTES), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        ex.connect(allh.cpu().numpy())
+    return ex

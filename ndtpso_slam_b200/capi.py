@@ -16,6 +16,7 @@ from . import build as _build
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_LIMIT = 0, -1, -2, -3, -4, -5
 OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREAD, OPT_CANDIDATE_BATCH, OPT_PIPELINE_CHUNKS = 1, 2, 3, 4, 5, 6, 7
 OPT_EXCHANGE_TIMEOUT_MS = 8
+OPT_HOT_CHUNK = 9
 KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 
 #: every symbol include/ndtpso_b200.h declares

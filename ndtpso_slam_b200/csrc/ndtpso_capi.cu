@@ -34,6 +34,7 @@ struct PoolBuf {
 };
 
 constexpr size_t kAlign = 256;
+constexpr int kDefaultHotChunk = 12;  // speculation window of the sliced kernel while gbest improves often (tools/chunk_sweep.py)
 inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -51,6 +52,7 @@ struct ndtpso_ctx {
   int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
   int opt_chunks = 1;      // pipelined align_batch: number of chunks (1 = off)
+  int opt_hot_chunk = -1;  // speculation window of the sliced kernel while gbest improves often: -1 auto, 0 off
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the most recent upload / results call
@@ -545,6 +547,9 @@ int launch_sliced_cfg(ndtpso_batch* bt, int nw, int groups, int smem) {
   }
   PsoParams prm = bt->prm;
   prm.smem_bytes = smem;
+  // one CTA per problem: rounds are cheap (two barriers), so a small window pays; a cluster round costs a cluster barrier
+  prm.hot_chunk = ctx->opt_hot_chunk >= 0 ? (ctx->opt_hot_chunk & 0xffff) : (CL == 1 ? kDefaultHotChunk : 0);
+  prm.hot_thresh = ctx->opt_hot_chunk >= 0x10000 ? (ctx->opt_hot_chunk >> 16) : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)bt->n * CL, 1, 1);
   cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
@@ -823,6 +828,10 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
     case NDTPSO_OPT_POINTS_PER_THREAD:
       if (value < 0 || value > kSlicedMaxNPT) return fail(ctx, NDTPSO_ERR_ARG, "points per thread out of range");
       ctx->opt_npt = (int)value;
+      return NDTPSO_OK;
+    case NDTPSO_OPT_HOT_CHUNK:
+      if (value < -1 || (value & 0xffff) > 4096 || value > 0xffffff) return fail(ctx, NDTPSO_ERR_ARG, "speculation window must be -1 (auto), 0 (off) or a particle count");
+      ctx->opt_hot_chunk = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_EXCHANGE_TIMEOUT_MS:
       if (value < 1 || value > 600000) return fail(ctx, NDTPSO_ERR_ARG, "exchange timeout must be in 1..600000 ms");

@@ -78,6 +78,8 @@ struct PsoParams {
   double w, c1, c2, wd;
   int n_draws;      // 3 + 3P + 6PI
   int smem_bytes;   // dynamic shared memory given to pso_kernel
+  int hot_chunk;    // point-sliced kernel: speculation window while gbest improves often (0 = always the whole swarm)
+  int hot_thresh;   // improvements in an iteration that keep the next one's window small
   PeerExchange ex;
 };
 

@@ -286,29 +286,40 @@ __device__ __forceinline__ void st_cluster_f64(const double* local, unsigned ran
 }
 
 // phase B: this warp scores the candidates [lo, hi) of `pose` that belong to its CTA's group on its
-// slice of the scan, JB candidates at a time.  The last batch is padded by re-scoring candidate
-// hi-1; padding results are not stored.  wpart[j*NW + warp] receives this warp's partial.
+// slice of the scan, JB candidates at a time.  wpart[j*NW + warp] receives this warp's partial.
+// One batch: candidates j .. j+JB-1 (clamped to hi-1; results of clamped slots are not stored).
+template <int NPT, int JB, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void score_batch(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, int j, int hi,
+                                            int NW, int warp, int lane) {
+  double acc[JB];
+  double2 txy[JB], cs[JB];
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+    const Pose* ps = pose + min(j + b, hi - 1);
+    txy[b] = *reinterpret_cast<const double2*>(&ps->x);
+    cs[b] = *reinterpret_cast<const double2*>(&ps->c);
+    acc[b] = 0.;
+  }
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b]);
+  }
+  const double tot = packed_warp_sum<JB>(acc, lane);
+  const int jj = j + packed_slot<JB>(lane);
+  if (packed_writer<JB>(lane) && jj < hi) wpart[jj * NW + warp] = tot;
+}
+
 template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
 __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, int lo,
                                                  int hi, const Topo& tp, int warp, int lane) {
-  for (int j = lo + tp.g * JB; j < hi; j += JB * tp.G) {
-    double acc[JB];
-    double2 txy[JB], cs[JB];
-#pragma unroll
-    for (int b = 0; b < JB; ++b) {
-      const Pose* ps = pose + min(j + b, hi - 1);
-      txy[b] = *reinterpret_cast<const double2*>(&ps->x);
-      cs[b] = *reinterpret_cast<const double2*>(&ps->c);
-      acc[b] = 0.;
-    }
-#pragma unroll
-    for (int b = 0; b < JB; ++b) {
-#pragma unroll
-      for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b]);
-    }
-    const double tot = packed_warp_sum<JB>(acc, lane);
-    const int jj = j + packed_slot<JB>(lane);
-    if (packed_writer<JB>(lane) && jj < hi) wpart[jj * tp.NW + warp] = tot;
+  if (CL == 1 && JB == 4) {
+    // whole batches of 4, then the 1..3 left over in batches of 2: a swarm of 70 costs 70 evaluations, not 72
+    int j = lo;
+    for (; j + 4 <= hi; j += 4) score_batch<NPT, 4, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
+    for (; j < hi; j += 2) score_batch<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
+  } else {
+    for (int j = lo + tp.g * JB; j < hi; j += JB * tp.G) score_batch<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
   }
 }
 
@@ -419,15 +430,22 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
 
   // ---- iterations
   int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0;
+  // Speculation window.  While gbest is improving often (the first iterations: every particle jumps towards gbest),
+  // a round speculates only on the next `win` particles, so an improvement discards at most a window's worth of
+  // evaluations instead of the rest of the swarm.  An iteration starts with the whole swarm as its window unless the
+  // previous one saw at least `hot_thresh` improvements.  Any window gives the reference's sequential order.
+  // After an improvement the window is `hot_chunk`; every round without one doubles it.
+  int hot = prm.hot_chunk > 0 ? 1 : 0, imp_it = 0, win = prm.hot_chunk;
   double w = prm.w;
   NDTPSO_PHASE_MARK(0)
   while (it < I) {
     Pose* pose = par ? pose1 : pose0;
     double* part = par ? part1 : part0;
+    const int lim = win > 0 ? min(P, start + win) : P;  // this round covers particles [start, lim)
     // phase A: owners of the pending particles [start, P)
     const int ja = start + ((tid - start) % T + T) % T;  // first pending particle owned by this thread
     const double* ucoef = sm.ubuf + (it & 1) * 6 * P;
-    for (int j = ja; j < P; j += T) {
+    for (int j = ja; j < lim; j += T) {
       double nx[3], nv[3];
       const double gb[3] = {gb0, gb1, gb2};
 #pragma unroll
@@ -452,20 +470,20 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     __syncthreads();
     NDTPSO_PHASE_MARK(1)
     if (start == 0) prefetch_draws(it + 1);  // first round of an iteration
-    score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, P, tp, warp, lane);  // phase B
+    score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, lim, tp, warp, lane);  // phase B
     NDTPSO_PHASE_MARK(2)
     if (CL == 1)
       __syncthreads();
     else
-      exchange_partials<JB, CL>(wpart, part, start, P, tp);
+      exchange_partials<JB, CL>(wpart, part, start, lim, tp);
     NDTPSO_PHASE_MARK(3)
     // phase C: j* = first pending particle that improves gbest (core.cpp:98)
     int jstar = -1;
     double cstar = 0.;
-    for (int base = start; base < P && jstar < 0; base += 32) {
+    for (int base = start; base < lim && jstar < 0; base += 32) {
       const int j = base + lane;
-      const double cj = (j < P) ? candidate_total(part, j, PW) : 0.;
-      const bool imp = (j < P) && (cj < gbc);
+      const double cj = (j < lim) ? candidate_total(part, j, PW) : 0.;
+      const bool imp = (j < lim) && (cj < gbc);
       const unsigned mask = __ballot_sync(0xffffffffu, imp);
       if (mask) {
         const int src = __ffs(mask) - 1;
@@ -473,7 +491,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
         cstar = __shfl_sync(0xffffffffu, cj, src);
       }
     }
-    const int end = (jstar >= 0) ? jstar + 1 : P;
+    const int end = (jstar >= 0) ? jstar + 1 : lim;
     for (int j = ja; j < end; j += T) {  // commit own particles in [start, end)  (core.cpp:89-96)
       const Pose ps = pose[j];
       const double cj = candidate_total(part, j, PW);
@@ -496,12 +514,19 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
       gb1 = pose[jstar].y;
       gb2 = pose[jstar].th;
       ++n_gb;
+      ++imp_it;
+      win = prm.hot_chunk;
+    } else if (win > 0) {
+      win = min(2 * win, 1 << 20);
     }
     start = end;
     if (start >= P) {
       start = 0;
       ++it;
       w = __dmul_rn(w, prm.wd);  // core.cpp:108
+      hot = (prm.hot_chunk > 0 && imp_it >= prm.hot_thresh) ? 1 : 0;
+      win = hot ? prm.hot_chunk : 0;
+      imp_it = 0;
     }
     par ^= 1;
     ++rounds;

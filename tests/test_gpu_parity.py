@@ -93,8 +93,24 @@ def test_deterministic_and_resolvable(golden, ctx):
     bt.close()
     assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
     assert np.abs(p1 - c["pose"]).max() <= POSE_ATOL
-    # rounds = iterations + gbest improvements that did not fall on an iteration's last particle
-    assert (st[:, 0] >= c["I"]).all() and (st[:, 0] <= c["I"] + st[:, 1]).all()
+    # every iteration takes at least one round; extra rounds come from gbest improvements (replays) and from the
+    # small speculation window the kernel uses while improvements are frequent
+    assert (st[:, 0] >= c["I"]).all() and (st[:, 1] >= 1).all()
+    # the speculation window is an optimisation only: any window gives bit-identical results
+    from ndtpso_slam_b200 import capi
+    for window in (0, 4 | (1 << 16), 16 | (2 << 16)):
+        cx = capi.Context(0)
+        cx.set_option(capi.OPT_HOT_CHUNK, window)
+        b2 = cx.batch(flats, conf_of(c))
+        b2.solve()
+        p3, c3 = b2.results()
+        s3 = b2.stats()
+        b2.close()
+        cx.close()
+        assert np.array_equal(p3, p1) and np.array_equal(c3, c1), window
+        assert np.array_equal(s3[:, 1], st[:, 1])  # the same gbest improvements, whatever the rounds
+        if window == 0:  # whole-swarm speculation: rounds = iterations + improvements not on an iteration's last particle
+            assert (s3[:, 0] <= c["I"] + s3[:, 1]).all()
 
 
 def test_oracle_on_fresh_inputs(oracle, ctx):

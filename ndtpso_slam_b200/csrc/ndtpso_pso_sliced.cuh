@@ -28,8 +28,13 @@ constexpr int kSlicedMaxNPT = 6;
 enum {
   VAR_FLOOR_ON_FP64 = 1,  // floor() by a round-down magic add on the fp64 pipe instead of F2I.F64.FLOOR (conversion pipe)
   VAR_KF_ON_FP64 = 2,     // k as a double by subtracting the magic constant (fp64 pipe) instead of I2F.F64
+  VAR_PIN_CONSTS = 4,     // keep 16/ln2 and 1/7! in vector registers (loaded through a lane-dependent address) instead of
+                          // re-materialising them from uniform registers with two moves per use: -4 instructions per evaluation
 };
-constexpr int kProdVariant = 0;
+#ifndef NDTPSO_PROD_VARIANT
+#define NDTPSO_PROD_VARIANT 4
+#endif
+constexpr int kProdVariant = NDTPSO_PROD_VARIANT;
 
 // Phase timing (tools/score_bench.cu builds with -DNDTPSO_PHASE_TIMING): thread 0 of every CTA adds the
 // cycles it spends in {prologue+init, phase A, phase B, phase C} (barrier waits included) to g_phase_cycles.
@@ -53,7 +58,11 @@ struct __align__(16) Pose {
 
 // Shared memory: [mbarrier 16][exp table 128][exp constants 64][records][grid] at FIXED offsets
 // (so the hot loop's table addresses are a constant and one register), then the swarm arrays.
+#if (NDTPSO_PROD_VARIANT & 4)
+constexpr int kSlicedTableOffset = 16 + (kExpTableSize + 8 + 64) * (int)sizeof(double);  // + per-lane copies of two constants
+#else
 constexpr int kSlicedTableOffset = 16 + (kExpTableSize + 8) * (int)sizeof(double);
+#endif
 
 struct SlicedSmem {
   uint64_t* bar;
@@ -169,12 +178,13 @@ __device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, 
   const double r1 = fma(d1, h11, d0 * h0.y);   // d0*S01 + d1*S11
   const double a = fma(r1, d1, r0 * d0);       // = -(d' S d)/2
   // fast_exp (fast_exp.h), with its constants in registers
-  const double kd = fma(a, m.l2e, kExpMagic);
+  const double l2e = m.l2e, c7 = m.c7;
+  const double kd = fma(a, l2e, kExpMagic);
   const int k = __double2loint(kd);
   const double kf = (VAR & VAR_KF_ON_FP64) ? (kd - kExpMagic) : static_cast<double>(k);
   double rr = fma(kf, m.ln2hi, a);
   rr = fma(kf, m.ln2lo, rr);
-  double pl = fma(rr, m.c7, m.c6);
+  double pl = fma(rr, c7, m.c6);
   pl = fma(pl, rr, m.c5);
   pl = fma(pl, rr, m.c4);
   pl = fma(pl, rr, m.c3);
@@ -564,6 +574,13 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   // constants go through volatile shared memory so the compiler keeps them in registers instead of
   // re-materialising 64-bit immediates inside the loop
   volatile double* cst = reinterpret_cast<volatile double*>(sm.cst);
+#if (NDTPSO_PROD_VARIANT & 4)
+  if (tid < 32) {
+    const ExpConsts ec = exp_consts();
+    sm.cst[8 + tid] = ec.l2e;
+    sm.cst[40 + tid] = ec.c7;
+  }
+#endif
   if (tid == 0) {
     const ExpConsts ec = exp_consts();
     cst[0] = ec.l2e;
@@ -602,10 +619,20 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   m.inv_cs = mp.inv_cs;
   m.hw_s = mp.hw * mp.inv_cs;
   m.hh_s = mp.hh * mp.inv_cs;
+#if (NDTPSO_PROD_VARIANT & 4)
+  {  // per-lane copies: a lane-dependent address is not uniform, so the two constants stay in vector registers
+    volatile double* lanes = reinterpret_cast<volatile double*>(sm.cst + 8);
+    m.l2e = lanes[tid & 31];
+    m.c7 = lanes[32 + (tid & 31)];
+  }
+#else
   m.l2e = cst[0];
+#endif
   m.ln2hi = cst[1];
   m.ln2lo = cst[2];
+#if !(NDTPSO_PROD_VARIANT & 4)
   m.c7 = cst[3];
+#endif
   m.c6 = cst[4];
   m.c5 = cst[5];
   m.c4 = cst[6];

@@ -11,6 +11,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -715,6 +716,19 @@ int launch_pso_any(ndtpso_batch* bt) {
   return rc;
 }
 
+// K1: the rand() streams of the problems that did not bring their own
+int launch_rng(ndtpso_batch* bt) {
+  ndtpso_ctx* ctx = bt->ctx;
+  const int grid = (bt->n + K1_WARPS - 1) / K1_WARPS;
+  if (bt->d_rng_state)
+    rng_fill_kernel<true><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(bt->d_probs, bt->n, bt->prm.n_draws, bt->d_rng_state);
+  else
+    rng_fill_kernel<false><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(bt->d_probs, bt->n, bt->prm.n_draws, nullptr);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return NDTPSO_OK;
+}
+
 int launch_compact(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   if (bt->n_maps == 0) return NDTPSO_OK;
@@ -902,9 +916,8 @@ int ndtpso_batch_solve(ndtpso_batch* bt) {
   if (rc) return rc;
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[1], ctx->stream));
   if (bt->any_device_rng) {
-    rng_fill_kernel<<<(bt->n + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, ctx->stream>>>(bt->d_probs, bt->n, bt->prm.n_draws, bt->d_rng_state);
-    CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches++;
+    rc = launch_rng(bt);
+    if (rc) return rc;
   }
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[2], ctx->stream));
   exchange_arm(bt);

@@ -165,7 +165,7 @@ __host__ __device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; 
 // row0..row0+nrows-1 so that the reference's FLAT index ix + gw*iy (including its wrap into the
 // next row when (x + W/2)/cs rounds up to gw, ndtframe.cpp:245) addresses it directly.
 // ------------------------------------------------------------------------------------------
-constexpr int K0_THREADS = 256;
+constexpr int K0_THREADS = 1024;
 
 __global__ void __launch_bounds__(K0_THREADS) compact_map_kernel(const DevMap* __restrict__ maps) {
   const DevMap& m = maps[blockIdx.x];
@@ -269,6 +269,7 @@ enum { K1_ST_NMOD = K1_RING, K1_ST_AHEAD, K1_ST_INIT, K1_ST_PAD, K1_STATE_WORDS 
 
 // `state` == nullptr: every problem's stream is that of srand(probs[b].seed).
 // `state` != nullptr: problem b continues the stream kept in state[b] (seeded with probs[b].seed on first use).
+template <bool PERSIST>
 __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProblem* __restrict__ probs, int n_problems, int n_draws,
                                                                  uint32_t* __restrict__ state) {
   __shared__ uint32_t ring_all[K1_WARPS][K1_RING];
@@ -278,12 +279,14 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
   if (probs[b].rnd_from_host) return;
   uint32_t* z = ring_all[warp];
   int* out = const_cast<int*>(probs[b].rnd);
-  uint32_t* st = state ? state + (size_t)b * K1_STATE_WORDS : nullptr;
+  uint32_t* st = PERSIST ? state + (size_t)b * K1_STATE_WORDS : nullptr;
 
-  int n_loc, ahead;  // next index to generate (ring coordinates, >= K1_RING); values generated but not handed out
-  if (st && st[K1_ST_INIT]) {
-    for (int i = lane; i < K1_RING; i += 32) z[i] = st[i];
-    n_loc = K1_RING + static_cast<int>(st[K1_ST_NMOD]);
+  // next index to generate, in ring coordinates: the same constant for a fresh and for a resumed stream (a saved ring is
+  // stored oldest value first and reloaded rotated), so every ring index below is a compile-time constant plus the lane
+  constexpr int n_loc = K1_RING + 373;
+  int ahead;  // values generated but not handed out yet
+  if (PERSIST && st[K1_ST_INIT]) {
+    for (int i = lane; i < K1_RING; i += 32) z[(n_loc + i) & (K1_RING - 1)] = st[i];
     ahead = static_cast<int>(st[K1_ST_AHEAD]);
     __syncwarp();
   } else {
@@ -307,8 +310,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
       if (lane < 3 && n + lane < 373) z[n + lane] = z[n + lane - 31] + z[n + lane - 3];
       __syncwarp();
     }
-    n_loc = K1_RING + 373;  // rand k = z[341 + k] >> 1: the first 32 are already in the history
-    ahead = 32;
+    ahead = 32;  // rand k = z[341 + k] >> 1: the first 32 are already in the history
   }
   // values that are already in the history
   for (int j = lane; j < min(ahead, n_draws); j += 32) out[j] = static_cast<int>(z[(n_loc - ahead + j) & (K1_RING - 1)] >> 1);
@@ -328,10 +330,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) rng_fill_kernel(const DevProble
     if (j < n_draws) out[j] = static_cast<int>(v >> 1);
     __syncwarp();
   }
-  if (st) {
-    for (int i = lane; i < K1_RING; i += 32) st[i] = z[i];
+  if (PERSIST) {
+    for (int i = lane; i < K1_RING; i += 32) st[i] = z[(n_loc + t0 + i) & (K1_RING - 1)];  // oldest first
     if (lane == 0) {
-      st[K1_ST_NMOD] = static_cast<uint32_t>((n_loc + t0) & (K1_RING - 1));
+      st[K1_ST_NMOD] = 0u;
       st[K1_ST_AHEAD] = static_cast<uint32_t>(ahead + t0 - n_draws);
       st[K1_ST_INIT] = 1u;
     }

@@ -137,8 +137,9 @@ int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problem
 
 /* The same call split in two so that a throughput-oriented caller can overlap the host-side staging
  * of batch k+1 with the GPU work of batch k:  submit = stage + H2D + kernel launches (asynchronous),
- * collect = D2H of the poses + synchronise + release.  Batches submitted on one context complete in
- * submission order. */
+ * collect = D2H of the poses + synchronise + release.  Consecutive submissions run on two alternating
+ * streams, so the kernels of batch k+1 fill the SMs batch k leaves idle while it drains; collect waits
+ * for its own batch only.  Results do not depend on what else is in flight. */
 int ndtpso_align_submit(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out);
 int ndtpso_align_collect(ndtpso_batch* batch, double* out_pose /* [n][3] */, double* out_cost /* [n] */);
 

@@ -46,6 +46,8 @@ struct ndtpso_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // pipelined align_batch
   cudaStream_t copy_stream = nullptr;  // uploads of batch k+1 overlap the kernels of batch k
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};  // ndtpso_align_submit alternates between them (see there)
+  unsigned pipe_next = 0;
   std::string err;
   int opt_warps = 0;
   int64_t opt_smem = 0;
@@ -808,6 +810,8 @@ void ndtpso_ctx_destroy(ndtpso_ctx* ctx) {
   for (auto& cs : ctx->chunk_stream)
     if (cs) cudaStreamDestroy(cs);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& ps : ctx->pipe_stream)
+    if (ps) cudaStreamDestroy(ps);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1048,9 +1052,26 @@ int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problem
 int ndtpso_align_submit(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_batch** out) {
   if (!ctx || !conf || !out) return fail(ctx, NDTPSO_ERR_ARG, "align_submit: null argument");
   *out = nullptr;
+  // Consecutive submissions on the context's own stream go to two alternating streams.  A batch of n CTAs rarely fills a
+  // whole number of waves (256 problems on 148 SMs x 2 CTAs leave 40 slots empty, and the SMs with one CTA finish early):
+  // with the next batch on another stream its CTAs take those slots at once instead of waiting for the kernel to drain.
+  cudaStream_t saved = ctx->stream;
+  const bool piped = ctx->stream == ctx->own_stream;
+  if (piped) {
+    cudaStream_t& ps = ctx->pipe_stream[ctx->pipe_next & 1u];
+    if (!ps) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    ctx->stream = ps;
+    ++ctx->pipe_next;
+  }
+  struct Restore {
+    ndtpso_ctx* c;
+    cudaStream_t s;
+    ~Restore() { c->stream = s; }
+  } restore{ctx, saved};
   ndtpso_batch* bt = nullptr;
   int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // stage (built cells only) + asynchronous H2D
   if (rc) return rc;
+  bt->no_cluster = piped && n >= 64;  // batches overlap: together they fill the GPU
   rc = ndtpso_batch_solve(bt);  // asynchronous launches
   if (rc == NDTPSO_OK && bt->n > 0) {
     // queue the read-back right behind the kernels (the head of the staging buffer is free again:

@@ -329,23 +329,18 @@ def _run_gpu_arm(args, real_stdout):
     if world > 1:
         exchange_kind = "NCCL all-gather of [B][4] fp64 poses per step"
         if args.exchange == "fused":
-            try:
+            exs = [sharding.make_exchange(ctx, B, world, rank, device="cuda") for _ in range(2)]  # None on every rank if IPC fails anywhere
+            if exs[0] is not None and exs[1] is not None:
                 for i in range(2):
-                    exs[i] = sharding.make_exchange(ctx, B, world, rank, device="cuda")
                     bts[i].attach_exchange(exs[i])
                 exchange_kind = ("peer stores of the [B][4] fp64 poses from the PSO kernel's epilogue into every rank's gathered buffer "
                                  "(NVLink, CUDA IPC) + arrival-flag wait kernel; verified against an NCCL all-gather")
-            except Exception as e:  # noqa: BLE001
-                print(f"rank {rank}: fused exchange unavailable ({e}); using NCCL", file=sys.stderr)
+            else:
+                print(f"rank {rank}: fused exchange unavailable (CUDA IPC); using the NCCL all-gather", file=sys.stderr)
+                for e_ in exs:
+                    if e_ is not None:
+                        e_.close()
                 exs = [None, None]
-        ok = torch.tensor([1 if exs[1] is not None else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if exs[1] is not None and int(ok.item()) == 0:
-            exs = [None, None]
-            exchange_kind = "NCCL all-gather of [B][4] fp64 poses per step"
-        if exs[1] is None:
-            for i in range(2):
-                bts[i].attach_exchange(None)
     ex = exs[0]
 
     def resident_step(i=0):

@@ -68,18 +68,44 @@ def solve_sharded(solve_fn, problems, world_size: int, rank: int, device=None, g
 def make_exchange(ctx, n_per_rank: int, world_size: int, rank: int, group=None, device=None):
     """The fused form of the exchange (include/ndtpso_b200.h, ndtpso_exchange_*): every rank allocates its gathered
     result buffer, the 64-byte CUDA IPC handles are all-gathered once, and from then on the PSO kernel's epilogue stores
-    each result into every rank's buffer over NVLink — no collective per step.  Returns a connected capi.Exchange."""
+    each result into every rank's buffer over NVLink — no collective per step.
+
+    Returns a connected capi.Exchange, or None ON EVERY RANK if any rank could not create or map the buffers (CUDA IPC
+    unavailable): the local steps that can fail are each followed by an all-reduce of a success flag, so the ranks never
+    diverge in the collectives they call."""
     import torch
     import torch.distributed as dist
 
     from . import capi
 
-    ex = capi.Exchange(ctx, world_size, rank, n_per_rank)
+    def all_ok(flag: bool) -> bool:
+        if world_size == 1:
+            return flag
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device if device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        return bool(int(t.item()))
+
+    ex = None
+    try:
+        ex = capi.Exchange(ctx, world_size, rank, n_per_rank)
+    except Exception:  # noqa: BLE001
+        ex = None
+    if not all_ok(ex is not None):
+        if ex is not None:
+            ex.close()
+        return None
     if world_size > 1:
         mine = torch.from_numpy(ex.handle.copy())
         if device is not None:
             mine = mine.to(device)
         allh = torch.empty((world_size, capi.IPC_HANDLE_BYTES), dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(allh, mine, group=group)
-        ex.connect(allh.cpu().numpy())
+        connected = True
+        try:
+            ex.connect(allh.cpu().numpy())
+        except Exception:  # noqa: BLE001
+            connected = False
+        if not all_ok(connected):
+            ex.close()
+            return None
     return ex

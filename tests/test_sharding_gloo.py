@@ -72,3 +72,20 @@ def test_sharded_solve_equals_single_rank(tmp_path, world, n_problems):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"pose_{r}.npy"), want_pose)
         assert np.array_equal(np.load(tmp_path / f"cost_{r}.npy"), want_cost)
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # no CUDA context here: creating the exchange fails on every rank, and make_exchange must come back with None on
+    # every rank after the SAME sequence of collectives (a rank that bailed out early would leave the others hanging)
+    ex = sharding.make_exchange(None, 4, world, rank)
+    open(os.path.join(out_dir, f"ex_{rank}.txt"), "w").write("none" if ex is None else "exchange")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_make_exchange_fails_on_all_ranks_together(tmp_path):
+    mp.spawn(_exchange_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ex_{r}.txt").read() for r in range(2)] == ["none", "none"]

@@ -276,3 +276,55 @@ def test_continuing_rand_stream(ctx, reference, oracle):
         assert rel_err(cost[0], wcost) <= SCORE_RTOL
         s_diff, s_prev, guess = want - s_prev, want, want
     df.close()
+
+
+def test_edge_cases_empty_scan_and_empty_map(ctx, reference, oracle):
+    """What the reference does with nothing to match: an empty map (every cost is 0, gbest never improves after the seed
+    particle) and an empty scan (loadLaser rejects every beam) — same poses as the oracle, no error, no status bit."""
+    from ndtpso_slam_b200.dframes import DeviceFrames, RNG_SEEDED
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    n = 3
+    df = DeviceFrames(ctx, n, S, S, cfg.cell_side, s.beams)
+    conf = capi.PsoConfig.make(population=9, iterations=4)
+    ranges = np.stack([_scan(cfg, (0.1, 0.0, 0.02), 40), np.zeros(s.beams, dtype=np.float32), _scan(cfg, (0., 0.1, 0.), 41)])
+    # 1) empty maps: nothing was ever merged
+    df.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+    assert [df.info(b)["scan_points"] for b in range(n)] == [len(_ref_scan_frame(reference, cfg, ranges[b]).flatten_points()) for b in range(n)]
+    assert df.info(1)["scan_points"] == 0
+    guess = np.array([[0.2, 0.08, 0.04]] * n)
+    pose, cost = df.align(guess, conf, RNG_SEEDED, [5, 6, 7])
+    geom = reference.frame(width=S, height=S, cell_side=cfg.cell_side).geometry()
+    ncell = geom["n_cells"]
+    empty = dict(geom, mean=np.zeros((ncell, 2)), inv_cov=np.zeros((ncell, 4)), built=np.zeros(ncell, dtype=np.uint8))
+    for b in range(n):
+        f = dict(empty, points=df.download_scan(b))
+        want, wcost, _ = oracle.pso(f, guess[b], syn.DEFAULT_DEVIATION, 9, 4, seed=5 + b)
+        assert np.array_equal(pose[b], want) and cost[b] == wcost == 0.0, b
+    # 2) merge the scans (frame 1 merges nothing), then match the same scans again: frame 1 has a map-less, scan-less problem
+    df.update(pose)
+    pose2, cost2 = df.align(None, conf, RNG_SEEDED, [8, 9, 10])
+    assert cost2[1] == 0.0 and cost2[0] < -50.0 and cost2[2] < -50.0
+    assert df.info(1)["created"] == 0 and df.info(0)["created"] > 20
+    assert not df.status().any()
+    df.close()
+
+
+def test_points_outside_the_map_are_dropped_like_the_reference(ctx, reference):
+    """A pose that throws most of the scan outside the 20 m frame: addPoint drops those points (getCellIndex == -1,
+    ndtframe.cpp:217-220); the device tables stay bit-identical to the reference's."""
+    from ndtpso_slam_b200.dframes import DeviceFrames
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    df = DeviceFrames(ctx, 1, S, S, cfg.cell_side, s.beams)
+    ref = reference.frame(width=S, height=S, cell_side=cfg.cell_side, init_windows=True)
+    for k, pose in enumerate([(0., 0., 0.), (6.5, -3.0, 0.7), (-9.0, 9.0, 2.0), (30.0, 30.0, 0.1)]):
+        f = _ref_scan_frame(reference, cfg, _scan(cfg, (0., 0., 0.), 60 + k))
+        ref.update(pose, f)
+        df.set_scan_points([f.flatten_points()])
+        df.update([pose])
+        ref.build()
+        df.build()
+        _assert_tables_equal(df.download_map(0), ref.flatten_map(), k)
+    assert not df.status().any()
+    df.close()

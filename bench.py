@@ -204,47 +204,71 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def run_tracking(ctx, B, conf, steps):
+def run_tracking(B, conf, steps, device, groups=2):
     """B robots, each tracked through the reference's per-scan callback (src/ndtpso_slam_node.cpp:177-244) with its map
     resident in HBM (include/ndtpso_dframes.h).  Robot b replays trajectory b of the bench workload: its map is seeded with
     the 5 map scans of synthetic.trajectory_problem(CFG2, b), then every timed step is one ndtpso_dframes_track_step call:
     H2D of the step's ranges (4 bytes per beam), loadLaser, NDTFrame::build + table compaction, rand() stream, PSO,
-    NDTFrame::update, D2H of the poses.  Steps are sequentially dependent (the pose of scan k positions scan k in the map
-    that scan k+1 is matched against), so nothing is pipelined; wall clock around the K calls."""
-    from ndtpso_slam_b200 import dframes, synthetic as syn
+    NDTFrame::update, D2H of the poses.  A robot's steps are sequentially dependent (the pose of scan k positions scan k in
+    the map that scan k+1 is matched against), so within a group nothing is pipelined; the robots are served as `groups`
+    independent groups, each by its own host thread, context and stream, so that one group's small kernels and host round
+    trips hide behind another group's PSO kernel.  Wall clock around the K steps of all groups."""
+    import threading
+
+    from ndtpso_slam_b200 import capi, dframes, synthetic as syn
     cfg = syn.CFG2
     s, S = cfg.sensor, cfg.map_size_m
     room = syn.Room(S)
-    df = dframes.DeviceFrames(ctx, B, S, S, cfg.cell_side, s.beams, max_cells=1024)
+    groups = max(1, min(groups, B // 96)) if B >= 96 else 1  # a group smaller than ~75 problems would be spread over clusters
+    bounds = [(g * B // groups, (g + 1) * B // groups) for g in range(groups)]
     sets = [syn.trajectory_problem(cfg, b) for b in range(B)]
-    for k in range(5):  # the map: 5 scans per robot merged at their known poses
-        df.load_laser(np.stack([ss.map_scans[k][1] for ss in sets]), s.angle_min, s.angle_increment, s.range_max)
-        df.update(np.array([ss.map_scans[k][0] for ss in sets]))
-    # the tracked scans: robot b moves on from its query pose, 2 cm and 1 mrad per scan
-    scans = []
-    for k in range(steps + 2):
-        scans.append(np.stack([syn.make_scan(room, s, (ss.true_pose[0] + 0.02 * k, ss.true_pose[1] + 0.005 * k, ss.true_pose[2] + 0.001 * k),
-                                             syn.NoiseLCG(777 + 131 * b + k)) for b, ss in enumerate(sets)]))
+    scans = [np.stack([syn.make_scan(room, s, (ss.true_pose[0] + 0.02 * k, ss.true_pose[1] + 0.005 * k, ss.true_pose[2] + 0.001 * k),
+                                     syn.NoiseLCG(777 + 131 * b + k)) for b, ss in enumerate(sets)]) for k in range(steps + 2)]
     init = np.array([ss.guess for ss in sets])
-    df.track_step(scans[0], s.angle_min, s.angle_increment, s.range_max, initial_poses=init, conf=conf)  # first scan: no matching
-    df.track_step(scans[1], s.angle_min, s.angle_increment, s.range_max, initial_poses=None, conf=conf)   # warm-up
-    kt = []
+    ctxs, dfs = [], []
+    for lo, hi in bounds:
+        c = capi.Context(device)
+        df = dframes.DeviceFrames(c, hi - lo, S, S, cfg.cell_side, s.beams, max_cells=1024)
+        for k in range(5):  # the map: 5 scans per robot merged at their known poses
+            df.load_laser(np.stack([ss.map_scans[k][1] for ss in sets[lo:hi]]), s.angle_min, s.angle_increment, s.range_max)
+            df.update(np.array([ss.map_scans[k][0] for ss in sets[lo:hi]]))
+        df.track_step(scans[0][lo:hi], s.angle_min, s.angle_increment, s.range_max, initial_poses=init[lo:hi], conf=conf)  # first scan: no matching
+        df.track_step(scans[1][lo:hi], s.angle_min, s.angle_increment, s.range_max, conf=conf)                            # warm-up
+        ctxs.append(c)
+        dfs.append(df)
+    poses = np.zeros((B, 3))
+    start = threading.Barrier(groups + 1)
+
+    def serve(g):
+        lo, hi = bounds[g]
+        start.wait()
+        for k in range(steps):
+            poses[lo:hi], _ = dfs[g].track_step(scans[2 + k][lo:hi], s.angle_min, s.angle_increment, s.range_max, conf=conf)
+
+    threads = [threading.Thread(target=serve, args=(g,)) for g in range(groups)]
+    for t in threads:
+        t.start()
+    start.wait()
     t0 = time.perf_counter()
-    for k in range(steps):
-        pose, cost = df.track_step(scans[2 + k], s.angle_min, s.angle_increment, s.range_max, initial_poses=None, conf=conf)
+    for t in threads:
+        t.join()
     wall = time.perf_counter() - t0
-    kt = df.kernel_times_ms()
+    kt = dfs[0].kernel_times_ms()
     true_last = np.array([(ss.true_pose[0] + 0.02 * (steps + 1), ss.true_pose[1] + 0.005 * (steps + 1), ss.true_pose[2] + 0.001 * (steps + 1))
                           for ss in sets])
-    err = np.abs(pose - true_last)
-    info = df.info(0)
-    flags = int(np.bitwise_or.reduce(df.status()))
-    out = {"value": B * steps / wall, "unit": "scan-matches/s", "robots": B, "steps": steps, "ms_per_step": 1e3 * wall / steps,
-           "h2d_bytes_per_step": int(B * s.beams * 4), "d2h_bytes_per_step": int(B * 32), "kernel_ms_last_step": kt,
-           "device_bytes": df.device_bytes(), "cells_created_robot0": info["created"], "cells_built_robot0": info["built"], "status_bits": flags,
+    err = np.abs(poses - true_last)
+    info = dfs[0].info(0)
+    flags = 0
+    for df in dfs:
+        flags |= int(np.bitwise_or.reduce(df.status()))
+    out = {"value": B * steps / wall, "unit": "scan-matches/s", "robots": B, "groups": groups, "steps": steps, "ms_per_step": 1e3 * wall / steps,
+           "h2d_bytes_per_step": int(B * s.beams * 4), "d2h_bytes_per_step": int(B * 32), "kernel_ms_last_step_group0": kt,
+           "device_bytes": sum(df.device_bytes() for df in dfs), "cells_created_robot0": info["created"], "status_bits": flags,
            "median_abs_pose_error_vs_truth": [float(v) for v in np.median(err, axis=0)],
            "api": "ndtpso_dframes_track_step: loadLaser + build + PSO 70x50 + update per call, maps resident in HBM"}
-    df.close()
+    for df, c in zip(dfs, ctxs):
+        df.close()
+        c.close()
     return out
 
 
@@ -466,7 +490,7 @@ def _run_gpu_arm(args, real_stdout):
     # ---- the per-scan callback with the maps resident in HBM: loadLaser -> align -> update
     tracking = None
     if rank == 0 and not args.no_tracking:
-        tracking = run_tracking(ctx, B, conf, steps=max(4, min(args.steps, 12)))
+        tracking = run_tracking(B, conf, steps=max(4, min(args.steps, 12)), device=local, groups=args.tracking_groups)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -533,6 +557,7 @@ def main():
     ap.add_argument("--ref-matches", type=int, default=4, help="CPU arm: matches per host worker per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tracking", action="store_true", help="skip the device-resident tracking leg")
+    ap.add_argument("--tracking-groups", type=int, default=2, help="tracking leg: independent groups of robots served by their own host thread and stream")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N > 1: how the solved poses reach every rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -120,7 +120,8 @@ enum {
   NDTPSO_OPT_CANDIDATE_BATCH = 6,  /* point-sliced kernel: candidates scored together (1, 2, 4); 0 = auto */
   NDTPSO_OPT_PIPELINE_CHUNKS = 7,  /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4, default 1) */
   NDTPSO_OPT_EXCHANGE_TIMEOUT_MS = 8, /* ndtpso_exchange_wait: give up after this long (default 10000) */
-  NDTPSO_OPT_HOT_CHUNK = 9 /* point-sliced kernel: particles speculated per round while gbest improves often; -1 auto, 0 = whole swarm */
+  NDTPSO_OPT_HOT_CHUNK = 9, /* point-sliced kernel: particles speculated per round while gbest improves often; -1 auto, 0 = whole swarm */
+  NDTPSO_OPT_SCREEN = 10    /* point-sliced kernel: fp32 lower-bound screen before the fp64 cost (results identical either way); -1 auto, 0 off */
 };
 int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value);
 
@@ -159,6 +160,8 @@ void* ndtpso_batch_device_results(ndtpso_batch* batch);
 int ndtpso_batch_results(ndtpso_batch* batch, double* out_pose /* [n][3] */, double* out_cost /* [n] */);
 /* per-problem counters after a solve: out[b] = {rounds, gbest_updates} */
 int ndtpso_batch_stats(ndtpso_batch* batch, int32_t* out /* [n][2] */);
+/* out[b] = {rounds, gbest_updates, fp64 cost evaluations, evaluations settled by the fp32 screen alone} */
+int ndtpso_batch_stats_ex(ndtpso_batch* batch, int32_t* out /* [n][4] */);
 /* device time of the last solve's kernels in ms, measured with CUDA events on the launch stream:
  * out_ms = {table compaction (K0), rand() stream (K1), PSO (K2)}; synchronises on the solve */
 int ndtpso_batch_kernel_times(ndtpso_batch* batch, double* out_ms /* [3] */);

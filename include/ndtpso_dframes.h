@@ -124,6 +124,8 @@ int ndtpso_dframes_download_scan(ndtpso_dframes* df, int32_t frame, double* poin
 /* out_i = {w_cells, h_cells, n_cells, created cells, built cells, scan points, align calls, status bits} */
 int ndtpso_dframes_info(ndtpso_dframes* df, int32_t frame, int32_t* out_i /* [8] */);
 int ndtpso_dframes_status(ndtpso_dframes* df, int32_t* flags /* [n_frames] */);
+/* counters of the last align, per frame: {rounds, gbest updates, fp64 cost evaluations, evaluations settled by the fp32 screen} */
+int ndtpso_dframes_pso_stats(ndtpso_dframes* df, int32_t* out /* [n_frames][4] */);
 /* device time in ms of the last call's kernels: {loadLaser, update, build (+compaction), rand() stream, PSO} */
 int ndtpso_dframes_kernel_times(ndtpso_dframes* df, double* out_ms /* [5] */);
 

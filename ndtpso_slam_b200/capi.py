@@ -17,6 +17,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_LIMIT = 0, -1, -2, -3, -4, -
 OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREAD, OPT_CANDIDATE_BATCH, OPT_PIPELINE_CHUNKS = 1, 2, 3, 4, 5, 6, 7
 OPT_EXCHANGE_TIMEOUT_MS = 8
 OPT_HOT_CHUNK = 9
+OPT_SCREEN = 10
 KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 
 #: every symbol include/ndtpso_b200.h declares
@@ -24,7 +25,7 @@ EXPORTS = [
     "ndtpso_abi_version", "ndtpso_pso_config_default", "ndtpso_device_count", "ndtpso_ctx_create", "ndtpso_ctx_destroy",
     "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch", "ndtpso_align_submit", "ndtpso_align_collect",
     "ndtpso_cost_batch", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
-    "ndtpso_batch_stats", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
+    "ndtpso_batch_stats", "ndtpso_batch_stats_ex", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
     "ndtpso_exchange_create", "ndtpso_exchange_connect", "ndtpso_exchange_connect_local", "ndtpso_batch_attach_exchange", "ndtpso_exchange_wait",
     "ndtpso_exchange_device_results", "ndtpso_exchange_results", "ndtpso_exchange_destroy",
 ]
@@ -95,6 +96,7 @@ def load_library(build_if_missing: bool = True):
     L.ndtpso_batch_device_results.restype = C.c_void_p
     L.ndtpso_batch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndtpso_batch_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndtpso_batch_stats_ex.argtypes = [C.c_void_p, C.c_void_p]
     L.ndtpso_batch_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
     L.ndtpso_batch_destroy.argtypes = [C.c_void_p]
     L.ndtpso_batch_destroy.restype = None
@@ -243,6 +245,12 @@ class Batch:
     def stats(self):
         out = np.zeros((self.n, 2), dtype=np.int32)
         self.ctx._check(self.ctx.lib.ndtpso_batch_stats(self.h, _ptr(out)))
+        return out
+
+    def stats_ex(self):
+        """[n, 4]: rounds, gbest updates, fp64 cost evaluations, evaluations settled by the fp32 screen alone."""
+        out = np.zeros((self.n, 4), dtype=np.int32)
+        self.ctx._check(self.ctx.lib.ndtpso_batch_stats_ex(self.h, _ptr(out)))
         return out
 
     def kernel_times_ms(self):

@@ -55,6 +55,7 @@ struct ndtpso_ctx {
   int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
   int opt_chunks = 1;      // pipelined align_batch: number of chunks (1 = off)
+  int opt_screen = -1;     // fp32 screening of the sliced kernel: -1 auto (on when the batch qualifies), 0 off, 1 on when it qualifies
   int opt_hot_chunk = -1;  // speculation window of the sliced kernel while gbest improves often: -1 auto, 0 off
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
@@ -93,6 +94,11 @@ struct ndtpso_batch {
   int* d_stats = nullptr;
   uint32_t* d_rng_state = nullptr;  // per-problem persistent rand() streams (device-resident frames), or nullptr
   ndtpso_exchange* ex = nullptr;    // results are also published to every rank's gathered buffer (multi-GPU)
+  // what the fp32 screen's error bound needs (ndtpso_pso_sliced.cuh): largest |coordinate| of any scan point, largest frame
+  // half-extent, largest 1/cell_side and grid width; scr_ok: every frame is whole cells of a power-of-two side, symmetric
+  double scr_pmax = 0., scr_ext = 0., scr_inv_cs = 0.;
+  int scr_gw = 0;
+  bool scr_ok = true;
   int need_dyn_smem = 0;  // points + records + grid of the largest problem
   int max_pts = 0;        // largest scan
   int max_table_smem = 0; // records + grid of the largest table
@@ -366,7 +372,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   const size_t o_extra_up = take(extra_upload_bytes);
   const size_t upload_bytes = off;
   const size_t o_out = take(sizeof(double) * 4 * (size_t)std::max(n, 1));
-  const size_t o_stats = take(sizeof(int) * 2 * (size_t)std::max(n, 1));
+  const size_t o_stats = take(sizeof(int) * kStatsWords * (size_t)std::max(n, 1));
   std::vector<size_t> o_hdr(M), o_grid(M), o_rec(M);
   for (int i = 0; i < M; ++i) {
     const ndtpso_map_view& m = *maps[i];
@@ -455,11 +461,20 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     map_dyn[i] = (sc.n_rec + 1) * 48 + round16((sc.nrows * m.w_cells + 1) * 2);
   });
   for (int i = 0; i < M; ++i) {
+    const ndtpso_map_view& mv = *maps[i];
+    const double wc = mv.width_m / mv.cell_side, hc = mv.height_m / mv.cell_side;
+    if (!(is_pow2_double(mv.cell_side) && mv.x_min == -mv.x_max && mv.y_min == -mv.y_max && wc == std::floor(wc) && hc == std::floor(hc) &&
+          mv.x_max == mv.width_m / 2. && mv.y_max == mv.height_m / 2.))
+      bt->scr_ok = false;
+    bt->scr_ext = std::max(bt->scr_ext, std::max(std::fabs(mv.x_max), std::fabs(mv.y_max)));
+    bt->scr_inv_cs = std::max(bt->scr_inv_cs, 1.0 / mv.cell_side);
+    bt->scr_gw = std::max(bt->scr_gw, std::max(mv.w_cells, mv.h_cells));
     bt->max_table_smem = std::max(bt->max_table_smem, map_dyn[i]);
     if (scans[i].n_rec > 65534) bt->all_compact = false;
     if (!scans[i].symmetric) bt->all_symmetric = false;
   }
   DevProblem* hp = reinterpret_cast<DevProblem*>(h + o_probs);
+  std::vector<double> pmax_of(std::max(n, 1), 0.);
   parallel_for(n, kHostThreads, [&](int b) {
     const ndtpso_problem& p = problems[b];
     DevProblem dp{};
@@ -476,7 +491,13 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     hp[b] = dp;
     if (p.n_points) memcpy(h + o_pts[b], p.points_xy, (size_t)p.n_points * 16);
     if (conf && p.rand_stream) memcpy(h + o_rnd[b], p.rand_stream, (size_t)prm.n_draws * 4);
+    double pm = 0.;
+    for (int i = 0; i < 2 * p.n_points; ++i) pm = std::max(pm, std::fabs(p.points_xy[i]));
+    pmax_of[b] = pm;  // NaN compares false and is caught below
+    for (int i = 0; i < 2 * p.n_points; ++i)
+      if (!(std::fabs(p.points_xy[i]) <= 1e30)) pmax_of[b] = INFINITY;
   });
+  for (int b = 0; b < n; ++b) bt->scr_pmax = std::max(bt->scr_pmax, pmax_of[b]);
   int need = 0;
   for (int b = 0; b < n; ++b) {
     need = std::max(need, problems[b].n_points * 16 + map_dyn[map_of[b]]);
@@ -538,8 +559,31 @@ int launch_pso(ndtpso_batch* bt, int smem) {
 // time; a problem may be spread over a cluster of CL CTAs (G candidate groups x S point slices).
 // launch_sliced returns 1 when the batch does not qualify (table too large for shared memory,
 // scan too long, > 65534 built cells, asymmetric Sigma^-1).
+// Constants of the fp32 screen's error bound for this batch (see ndtpso_pso_sliced.cuh); false = the batch does not qualify.
+//   dx: error of a transformed point's coordinate in fp32.  For a point that ends up inside a frame, |t| <= ext + 2 pmax, so
+//       inputs (p, cos, sin, t rounded to fp32: 2^-24 relative each) and the two FMAs give at most 2^-24 (6 pmax + 3 ext);
+//       taken as 2^-23 (8 pmax + 4 ext).
+//   dd: error of its offset from a cell mean: dx + rounding of the mean and of the subtraction; doubled for safety.
+//   beta: band around cell edges inside which fp32 and fp64 may pick different cells: 8x the error of the cell coordinate.
+bool screen_params(const ndtpso_batch* bt, PsoParams* prm) {
+  prm->screen = 0;
+  const ndtpso_ctx* ctx = bt->ctx;
+  if (ctx->opt_screen == 0 || !bt->scr_ok || !(bt->scr_pmax <= 1e6) || !(bt->scr_ext > 0.) || bt->scr_gw >= (1 << 20)) return false;
+  const double u23 = 1.1920928955078125e-07;  // 2^-23
+  const double pmax = std::max(bt->scr_pmax, 1.0), ext = bt->scr_ext;
+  const double dx = u23 * (8. * pmax + 4. * ext);
+  const double dd = 2. * (dx + u23 * ext);
+  const double du = dx * bt->scr_inv_cs + u23 * bt->scr_gw;
+  const double beta = std::max(1e-3, 8. * du);
+  if (beta > 0.05) return false;
+  prm->screen = 1;
+  prm->scr_dd2 = (float)(dd * dd * 1.000001);
+  prm->scr_beta_c = (float)(0.5 - beta);
+  return true;
+}
+
 template <int NPT, int JB, int CL, int MAXT, int MINB>
-int launch_sliced_cfg(ndtpso_batch* bt, int nw, int groups, int smem) {
+int launch_sliced_cfg(ndtpso_batch* bt, int nw, int groups, int smem, bool screen = false) {
   ndtpso_ctx* ctx = bt->ctx;
   auto kern = pso_sliced_kernel<NPT, JB, CL, MAXT, MINB>;
   static bool attr_set[64] = {false};
@@ -553,6 +597,7 @@ int launch_sliced_cfg(ndtpso_batch* bt, int nw, int groups, int smem) {
   // one CTA per problem: rounds are cheap (two barriers), so a small window pays; a cluster round costs a cluster barrier
   prm.hot_chunk = ctx->opt_hot_chunk >= 0 ? (ctx->opt_hot_chunk & 0xffff) : (CL == 1 ? kDefaultHotChunk : 0);
   prm.hot_thresh = ctx->opt_hot_chunk >= 0x10000 ? (ctx->opt_hot_chunk >> 16) : 1;
+  if (!(CL == 1 && screen && screen_params(bt, &prm))) prm.screen = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)bt->n * CL, 1, 1);
   cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
@@ -662,7 +707,15 @@ int launch_sliced(ndtpso_batch* bt) {
   }
   if (npt < 1 || npt > kSlicedMaxNPT || nw > kSlicedMaxWarps[npt]) return 1;
   nw = std::max(nw, 4);
-  const int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem));
+  PsoParams probe{};
+  bool scr = npt == 3 && (ctx->opt_cand_batch == 0 || ctx->opt_cand_batch == 4) && screen_params(bt, &probe);  // the default shape only
+  const int smem_plain = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, 0));
+  int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, scr ? 1 : 0));
+  // not at the price of the second CTA per SM, and not beyond what a CTA may have
+  if (scr && (smem > ctx->max_smem_optin || (smem > ctx->max_smem_optin / 2 && smem_plain <= ctx->max_smem_optin / 2))) {
+    scr = false;
+    smem = smem_plain;
+  }
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;
   switch (npt) {
@@ -671,7 +724,7 @@ int launch_sliced(ndtpso_batch* bt) {
     case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 1, 640, 1>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<2, 2, 1, 640, 1>(bt, nw, 1, smem)
                                                                                         : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem);
     case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem)
-                                                                                        : launch_sliced_cfg<3, 4, 1, 384, 2>(bt, nw, 1, smem);
+                                                                                        : launch_sliced_cfg<3, 4, 1, 384, 2>(bt, nw, 1, smem, scr);
     case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem);
     case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem);
     default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem);
@@ -847,6 +900,10 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
       if (value < 0 || value > kSlicedMaxNPT) return fail(ctx, NDTPSO_ERR_ARG, "points per thread out of range");
       ctx->opt_npt = (int)value;
       return NDTPSO_OK;
+    case NDTPSO_OPT_SCREEN:
+      if (value < -1 || value > 1) return fail(ctx, NDTPSO_ERR_ARG, "screen must be -1 (auto), 0 (off) or 1 (on)");
+      ctx->opt_screen = (int)value;
+      return NDTPSO_OK;
     case NDTPSO_OPT_HOT_CHUNK:
       if (value < -1 || (value & 0xffff) > 4096 || value > 0xffffff) return fail(ctx, NDTPSO_ERR_ARG, "speculation window must be -1 (auto), 0 (off) or a particle count");
       ctx->opt_hot_chunk = (int)value;
@@ -977,7 +1034,21 @@ int ndtpso_batch_stats(ndtpso_batch* bt, int32_t* out) {
   ndtpso_ctx* ctx = bt->ctx;
   if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_stats before batch_solve");
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpy(out, bt->d_stats, sizeof(int) * 2 * (size_t)bt->n, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> all((size_t)kStatsWords * bt->n);
+  CUDA_TRY(ctx, cudaMemcpy(all.data(), bt->d_stats, sizeof(int) * kStatsWords * (size_t)bt->n, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < bt->n; ++b) {
+    out[2 * b] = all[(size_t)kStatsWords * b];
+    out[2 * b + 1] = all[(size_t)kStatsWords * b + 1];
+  }
+  return NDTPSO_OK;
+}
+
+int ndtpso_batch_stats_ex(ndtpso_batch* bt, int32_t* out) {
+  if (!bt || !out) return NDTPSO_ERR_ARG;
+  ndtpso_ctx* ctx = bt->ctx;
+  if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_stats before batch_solve");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(out, bt->d_stats, sizeof(int) * kStatsWords * (size_t)bt->n, cudaMemcpyDeviceToHost));
   return NDTPSO_OK;
 }
 

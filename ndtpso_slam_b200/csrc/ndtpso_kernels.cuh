@@ -64,6 +64,7 @@ struct DevProblem {
 // kernel, the CTA that solved problem b stores its 32-byte result straight into the gathered result
 // buffer of EVERY rank (its own and, over NVLink, its peers'), and the last CTA of the launch raises
 // this rank's arrival flag on every rank.  world == 0: off.
+constexpr int kStatsWords = 4;  // per problem: rounds, gbest updates, fp64 cost evaluations, evaluations settled by the fp32 screen
 constexpr int kMaxPeers = 8;
 struct PeerExchange {
   double* out[kMaxPeers];     // rank r's gathered buffer [world * n_per_rank][4] (this epoch's half)
@@ -80,6 +81,10 @@ struct PsoParams {
   int smem_bytes;   // dynamic shared memory given to pso_kernel
   int hot_chunk;    // point-sliced kernel: speculation window while gbest improves often (0 = always the whole swarm)
   int hot_thresh;   // improvements in an iteration that keep the next one's window small
+  // fp32 screening of the point-sliced kernel (ndtpso_pso_sliced.cuh): 0 = off
+  int screen;
+  float scr_dd2;    // delta_d^2: square of the bound on the fp32 error of a transformed point's offset from a cell mean
+  float scr_beta_c; // 0.5 - beta: a point closer than beta cell sides to a cell edge counts as worst case
   PeerExchange ex;
 };
 
@@ -679,6 +684,8 @@ __device__ __forceinline__ void pso_body(const Cost& cost, const DevProblem& pr,
     if (stats) {
       stats[0] = rounds;
       stats[1] = n_gb;
+      stats[2] = 0;
+      stats[3] = 0;
     }
   }
 }
@@ -783,7 +790,7 @@ __global__ void __launch_bounds__(NW * 32) pso_kernel(const DevProblem* __restri
   PsoSmem sm = carve_smem(smem_raw, prm.P);
   const Staged st = stage_problem(pr, mp, sm.dyn, prm.smem_bytes - sm.fixed_bytes, sm.etab, sm.bar);
   double* o = out + 4 * (size_t)b;
-  int* s = stats ? stats + 2 * (size_t)b : nullptr;
+  int* s = stats ? stats + kStatsWords * (size_t)b : nullptr;
   if (st.mode == COST_FAST_GEOM) {
     pso_body<CostOf<COST_FAST_GEOM>, NW>(CostOf<COST_FAST_GEOM>{st.fast}, pr, prm, sm, o, s);
   } else if (st.mode == COST_FAST_ANY) {

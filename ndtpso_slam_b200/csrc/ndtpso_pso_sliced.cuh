@@ -79,6 +79,11 @@ struct SlicedSmem {
   double* vnew;     // [P][3]
   double* pb;       // [P][3]
   double* pbc;      // [P]
+  // fp32 screening (CL == 1 only; null when off)
+  float4* pose32;   // [P+1] {x, y, cos, sin} of the current round's candidates
+  float* lbpart;    // [(P+1)*NW] per-warp partial sums of the upper bounds
+  int* surv;        // [P+2] candidates that need the fp64 evaluation; surv[P+1] = their number
+  float* rec32;     // [(n_rec+1)][8] {h00, h01, h11, hs, mx, my, -, -}
 };
 
 // PW = partials per candidate summed in phase C; WP = warp partials per candidate of the cluster form (0 when CL == 1)
@@ -92,12 +97,18 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   b += Pn * 13 * (int)sizeof(double);
   return (b + 15) & ~15;
 }
-// total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2)
-__host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int table_bytes) {
-  return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP);
+// shared memory of the fp32 screen without its record table: pose32, lbpart, surv
+__host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
+  return (P + 1) * 16 + round16((P + 1) * NW * 4) + round16((P + 2) * 4);
+}
+// total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2).  With the screen the fp32 records take
+// (n_rec + 1) * 32 bytes more, at most two thirds of table_bytes.
+__host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int table_bytes, int screen = 0) {
+  return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP) +
+         (screen ? sliced_screen_fixed_bytes(P, PW) + round16(table_bytes * 2 / 3 + 16) : 0);
 }
 
-__device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int PW, int WP, int table_bytes) {
+__device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int PW, int WP, int table_bytes, int screen = 0) {
   SlicedSmem s;
   const int Pn = P > 0 ? P : 1;
   s.bar = reinterpret_cast<uint64_t*>(base);
@@ -121,6 +132,20 @@ __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, i
   s.vnew = d + 6 * Pn;
   s.pb = d + 9 * Pn;
   s.pbc = d + 12 * Pn;
+  s.pose32 = nullptr;
+  s.lbpart = nullptr;
+  s.surv = nullptr;
+  s.rec32 = nullptr;
+  if (screen) {
+    p = base + kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP);
+    s.pose32 = reinterpret_cast<float4*>(p);
+    p += (P + 1) * 16;
+    s.lbpart = reinterpret_cast<float*>(p);
+    p += round16((P + 1) * PW * 4);
+    s.surv = reinterpret_cast<int*>(p);
+    p += round16((P + 2) * 4);
+    s.rec32 = reinterpret_cast<float*>(p);
+  }
   return s;
 }
 
@@ -266,6 +291,139 @@ __device__ __forceinline__ bool packed_writer(int lane) {
   return (lane & (32 / JB - 1)) == 0;
 }
 
+// ---- fp32 screen ------------------------------------------------------------------------------------
+// 9 of 10 candidate poses a swarm evaluates cannot improve their particle's best (median cost ratio 0.23), and the PSO only
+// ever asks "is this cost below pbest?" of them (core.cpp:94): their exact value is never used.  So every pending candidate
+// is first bounded in fp32 — a RIGOROUS lower bound L <= cost — and only those with L < pbest get the fp64 evaluation.
+// Results are bit-identical with the screen on or off: a candidate is dropped only when its fp64 cost provably fails the
+// comparison, and survivors are evaluated exactly as before.
+//
+// The bound, per scan point.  Let H = Sigma^-1/2 (positive semi-definite; the host only selects this kernel for such
+// tables), A(d) = d'Hd, so the point's term is -exp(-A(d*)) with d* its exact offset from the cell mean.
+//   * Position.  The fp32 transform is within delta_d of the fp64 one in each coordinate (delta_d from the magnitudes of
+//     the scan, the frame and fp32 rounding; PsoParams::scr_dd2 = delta_d^2).
+//   * Cell.  If the fp32 point lies within beta cell sides of a cell edge (which includes the frame's border: frames are
+//     whole cells), fp32 and fp64 may disagree on the cell: the point counts as the worst case, exp(.) = 1.  Otherwise both
+//     pick the same cell c, and |d_k| <= dmax_k(c), the distance from the mean to the far side of the cell.
+//   * Exponent.  With d = d* + eps, |eps_k| <= delta_d, and Cauchy-Schwarz + AM-GM on the cross term,
+//         A(d*) >= (1 - t) A(d) - A(eps)/t,          A(eps) <= hs delta_d^2,   hs = H00 + 2|H01| + H11.
+//     A(d) = z0^2 + z1^2 with z = L'd (Cholesky factor L of H).  In fp32 (factor rounded, two FMAs) each z_k is off by at
+//     most ez_k = 3 * 2^-24 * (sum of |L_kj| dmax_j), and (|z| - ez)^2 >= (1 - t) z^2 - ez^2/t, and the sum of the two
+//     squares carries 2^-22 relative rounding.  Together, with t chosen per record (sqrt of the absolute terms, clamped to
+//     [2^-10, 2^-3]: it balances the relative loosening t A against the absolute one for A of order one):
+//         -A(d*) <= -(1 - t)^2 (1 - 2^-22) Atilde + kappa,     kappa = (ez0^2 + ez1^2)/t + hs delta_d^2 / t
+//     The record stores L scaled by sqrt((1 - t)^2 (1 - 2^-22) log2(e)) and kappa log2(e): the screen evaluates
+//         e = ex2(min(kappa2 - z0~^2 - z1~^2, 0)) >= exp(-A(d*)).
+//     The null record (unbuilt cell, outside the strip) has kappa2 = -1e30: e = 0 without a test.
+//   * ex2.approx (2 ulp), the fp32 product/sums of the accumulation: a 2^-14 slack on the total, and 1e-6 absolute for
+//     results flushed to zero:  L = -(sum (1 + 2^-14)) - 1e-6.
+// cost >= L because each fp64 term is >= -(upper bound of its exponential).
+struct ScreenCtx {
+  const float* rec32;          // shared: [n_rec + 1][8] = {l00, l10, l11, kappa2, mx, my, -, -}
+  const unsigned short* grid;  // shared
+  float x_max, y_max, inv_cs, off_u, off_v;  // off = (W/2)/cs - 0.5: the cell coordinate minus one half
+  float beta_c;                              // 0.5 - beta
+  int gw, span;
+  unsigned base;
+};
+
+constexpr float kScreenMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to an integer
+constexpr int kScreenMagicBits = 0x4B400000;     // its bit pattern
+
+__device__ __forceinline__ void screen_point(const ScreenCtx& m, const float2 p, const float4 ps, float& acc) {
+  const float x = fmaf(p.x, ps.z, fmaf(-p.y, ps.w, ps.x));
+  const float y = fmaf(p.x, ps.w, fmaf(p.y, ps.z, ps.y));
+  const bool inb = (fabsf(x) < m.x_max) && (fabsf(y) < m.y_max);  // only trusted away from the cell edges
+  const float uh = fmaf(x, m.inv_cs, m.off_u), vh = fmaf(y, m.inv_cs, m.off_v);  // cell coordinate - 0.5
+  const float tu = uh + kScreenMagic, tv = vh + kScreenMagic;  // round to nearest of (u - 0.5) = floor(u), for |u| < 2^22
+  // distance of the fractional part from 0.5: beyond 0.5 - beta means within beta of an edge
+  const bool unc = (fabsf(uh - (tu - kScreenMagic)) > m.beta_c) || (fabsf(vh - (tv - kScreenMagic)) > m.beta_c);
+  // ix + gw*iy - base with ix = bits(tu) - magic bits: the constants are folded into `base`
+  const unsigned g = __float_as_uint(tu) + static_cast<unsigned>(m.gw) * __float_as_uint(tv) - m.base;  // wraps like the folded constants
+  const bool in_strip = inb && (g < static_cast<unsigned>(m.span));
+  const unsigned r = m.grid[in_strip ? g : static_cast<unsigned>(m.span)];
+  const float* q = m.rec32 + 8 * r;
+  const float4 l = *reinterpret_cast<const float4*>(q);  // l00, l10, l11, kappa2
+  const float2 mu = *reinterpret_cast<const float2*>(q + 4);
+  const float d0 = x - mu.x, d1 = y - mu.y;
+  const float z0 = fmaf(l.y, d1, l.x * d0);
+  const float z1 = l.z * d1;
+  const float xe = fmaf(-z1, z1, fmaf(-z0, z0, l.w));
+  float e;  // ex2.approx: 2 ulp, results below 2^-126 flushed to zero; both covered by the total's slack
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(xe, 0.f)));
+  acc += unc ? 1.0f : e;
+}
+
+// warp sums of JB per-lane accumulators, packed like packed_warp_sum (same slot assignment)
+template <int JB>
+__device__ __forceinline__ float packed_warp_sum_f(const float (&a)[JB], int lane);
+template <>
+__device__ __forceinline__ float packed_warp_sum_f<2>(const float (&a)[2], int lane) {
+  const bool hi16 = (lane & 16) != 0;
+  float k = hi16 ? a[1] : a[0];
+  k += __shfl_xor_sync(0xffffffffu, hi16 ? a[0] : a[1], 16);
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+  return k;
+}
+template <>
+__device__ __forceinline__ float packed_warp_sum_f<4>(const float (&a)[4], int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  float k01 = hi16 ? a[1] : a[0];
+  k01 += __shfl_xor_sync(0xffffffffu, hi16 ? a[0] : a[1], 16);
+  float k23 = hi16 ? a[3] : a[2];
+  k23 += __shfl_xor_sync(0xffffffffu, hi16 ? a[2] : a[3], 16);
+  float k = hi8 ? k23 : k01;
+  k += __shfl_xor_sync(0xffffffffu, hi8 ? k01 : k23, 8);
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+  return k;
+}
+
+// screen of candidates j .. j+JB-1 (clamped to hi-1) on this warp's slice: lbpart[j*NW + warp] = sum of the upper bounds
+template <int NPT, int JB>
+__device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&pf)[NPT], const float4* pose32, float* lbpart, int j, int hi,
+                                             int NW, int warp, int lane) {
+  float acc[JB];
+  float4 ps[JB];
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+    ps[b] = pose32[min(j + b, hi - 1)];
+    acc[b] = 0.f;
+  }
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) screen_point(m, pf[k], ps[b], acc[b]);
+  }
+  const float tot = packed_warp_sum_f<JB>(acc, lane);
+  const int jj = j + packed_slot<JB>(lane);
+  if (packed_writer<JB>(lane) && jj < hi) lbpart[jj * NW + warp] = tot;
+}
+
+// fp64 evaluation of the candidates listed in surv[i .. i+JB-1] (clamped to the last entry)
+template <int NPT, int JB, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void score_batch_listed(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, const int* surv,
+                                                   int i, int ns, int NW, int warp, int lane) {
+  double acc[JB];
+  double2 txy[JB], cs[JB];
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+    const Pose* ps = pose + surv[min(i + b, ns - 1)];
+    txy[b] = *reinterpret_cast<const double2*>(&ps->x);
+    cs[b] = *reinterpret_cast<const double2*>(&ps->c);
+    acc[b] = 0.;
+  }
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b]);
+  }
+  const double tot = packed_warp_sum<JB>(acc, lane);
+  const int ii = i + packed_slot<JB>(lane);
+  if (packed_writer<JB>(lane) && ii < ns) wpart[surv[ii] * NW + warp] = tot;
+}
+
 // ---- thread-block cluster support -------------------------------------------------------------
 // A problem may be solved by a cluster of CL CTAs (one per SM) when the batch is too small to fill
 // the GPU: the CTAs are arranged as G candidate groups x S point slices (CL = G*S).  CTA (g, s)
@@ -371,8 +529,9 @@ __device__ __forceinline__ double candidate_total(const double* part, int j, int
 }
 
 template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
-__device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&pt)[NPT], const DevProblem& pr, const PsoParams& prm,
-                                            const SlicedSmem& sm, const Topo& tp, double* __restrict__ out, int* __restrict__ stats) {
+__device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& sc, const bool scr, const double2 (&pt)[NPT],
+                                            const DevProblem& pr, const PsoParams& prm, const SlicedSmem& sm, const Topo& tp,
+                                            double* __restrict__ out, int* __restrict__ stats) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int P = prm.P, I = prm.I, PW = tp.PW;
@@ -439,7 +598,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
   }
 
   // ---- iterations
-  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0;
+  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0, n_f64 = P + 1, n_scr = 0;
   // Speculation window.  While gbest is improving often (the first iterations: every particle jumps towards gbest),
   // a round speculates only on the next `win` particles, so an improvement discards at most a window's worth of
   // evaluations instead of the rest of the swarm.  An iteration starts with the whole swarm as its window unless the
@@ -473,6 +632,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
       double s, c;
       sincos(nx[2], &s, &c);
       pose[j] = Pose{nx[0], nx[1], c, s, nx[2], 0.};
+      if (CL == 1 && scr) sm.pose32[j] = make_float4(static_cast<float>(nx[0]), static_cast<float>(nx[1]), static_cast<float>(c), static_cast<float>(s));
       sm.vnew[3 * j] = nv[0];
       sm.vnew[3 * j + 1] = nv[1];
       sm.vnew[3 * j + 2] = nv[2];
@@ -480,7 +640,55 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     __syncthreads();
     NDTPSO_PHASE_MARK(1)
     if (start == 0) prefetch_draws(it + 1);  // first round of an iteration
-    score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, lim, tp, warp, lane);  // phase B
+    if (CL == 1 && FAST_GEOM && scr) {
+      // phase B1: fp32 lower bound of every pending candidate's cost on this warp's slice
+      float2 pf[NPT];
+#pragma unroll
+      for (int k = 0; k < NPT; ++k)  // padding points (1e200, 0) become (1e30, 0): still outside every frame, but finite in fp32
+        pf[k] = make_float2(static_cast<float>(fmin(pt[k].x, 1e30)), static_cast<float>(pt[k].y));
+      {
+        int j = start;
+        for (; j + 4 <= lim; j += 4) screen_batch<NPT, 4>(sc, pf, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
+        for (; j < lim; j += 2) screen_batch<NPT, 2>(sc, pf, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
+      }
+      __syncthreads();
+      // warp 0 lists the candidates whose bound does not already rule out an improvement of their particle's best
+      // (core.cpp:94); the others get a cost of +1e300, which phase C treats like any cost that improves nothing
+      if (warp == 0) {
+        int ns = 0;
+        for (int base = start; base < lim; base += 32) {
+          const int j = base + lane;
+          bool alive = false;
+          if (j < lim) {
+            double u = 0.;
+            for (int w2 = 0; w2 < tp.NW; ++w2) u += static_cast<double>(sm.lbpart[j * tp.NW + w2]);
+            const double lower = -(u * (1. + 6.103515625e-5)) - 1e-6;  // slack: ex2.approx, fp32 products and sums (2^-14), flushed denormals
+            alive = !(lower >= sm.pbc[j]);
+            if (!alive) {
+              part[j * PW] = 1e300;
+              for (int w2 = 1; w2 < PW; ++w2) part[j * PW + w2] = 0.;
+            }
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, alive);
+          if (alive) sm.surv[ns + __popc(mask & ((1u << lane) - 1u))] = j;
+          ns += __popc(mask);
+        }
+        if (lane == 0) sm.surv[P + 1] = ns;
+      }
+      __syncthreads();
+      // phase B2: the fp64 evaluation of the survivors
+      const int ns = sm.surv[P + 1];
+      n_f64 += ns;
+      n_scr += (lim - start) - ns;
+      {
+        int i = 0;
+        for (; i + 4 <= ns; i += 4) score_batch_listed<NPT, 4, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
+        for (; i < ns; i += 2) score_batch_listed<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
+      }
+    } else {
+      n_f64 += lim - start;
+      score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, lim, tp, warp, lane);  // phase B
+    }
     NDTPSO_PHASE_MARK(2)
     if (CL == 1)
       __syncthreads();
@@ -551,6 +759,8 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
     if (stats) {
       stats[0] = rounds;
       stats[1] = n_gb;
+      stats[2] = n_f64;
+      stats[3] = n_scr;
     }
   }
   if (CL > 1) cluster_barrier();  // no CTA may exit while peers can still store into its shared memory
@@ -561,14 +771,15 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&p
 // (coalesced 16-byte loads), and fills the loop-invariant context.
 template <int NPT>
 __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, const DevProblem& pr, const DevMap& mp, int P, const Topo& tp,
-                                                      SliceCtx& m, double2 (&pt)[NPT]) {
+                                                      SliceCtx& m, double2 (&pt)[NPT], int screen = 0, ScreenCtx* sc = nullptr,
+                                                      const PsoParams* prm = nullptr) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int n_rec = mp.hdr[HDR_NREC];
   const int row0 = mp.hdr[HDR_ROW0], nrows = mp.hdr[HDR_NROWS];
   const int span = nrows * mp.gw;
   const int rec_bytes = (n_rec + 1) * 48;
   const int grid_bytes = round16((span + 1) * 2);
-  const SlicedSmem sm = carve_sliced(smem_raw, P, tp.PW, tp.CL == 1 ? 0 : tp.NW, rec_bytes + grid_bytes);
+  const SlicedSmem sm = carve_sliced(smem_raw, P, tp.PW, tp.CL == 1 ? 0 : tp.NW, rec_bytes + grid_bytes, screen);
 
   if (tid < kExpTableSize) sm.etab[tid] = c_exp_table[tid];
   // constants go through volatile shared memory so the compiler keeps them in registers instead of
@@ -642,6 +853,60 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   m.span = span;
   m.null_id = n_rec;
   mbar_wait(sm.bar, 0);
+  if (screen) {
+    // fp32 records of the screen (see above): one per built cell, found through the grid so that the cell's extent is
+    // known.  Read after the next __syncthreads (the body has one before its first use).
+    const double* rec = reinterpret_cast<const double*>(sm.table);
+    const double dd2 = static_cast<double>(prm->scr_dd2);
+    const double dd = sqrt(dd2);
+    const double u24 = 5.9604644775390625e-08;
+    for (int g = tid; g <= span; g += T) {
+      const int r = (g < span) ? m.grid[g] : n_rec;
+      if (g < span && r == n_rec) continue;  // unbuilt cell
+      float* o = sm.rec32 + 8 * r;
+      if (r == n_rec) {  // the null record
+        o[0] = o[1] = o[2] = 0.f;
+        o[3] = -1e30f;
+        o[4] = o[5] = o[6] = o[7] = 0.f;
+        continue;
+      }
+      const double* q = rec + 6 * r;
+      const double mx = q[0], my = q[1], H00 = -q[2], H01 = -q[3], H11 = -q[5];
+      const int cell = g + row0 * mp.gw;
+      const double cx = (cell % mp.gw) * mp.cs - mp.hw, cy = (cell / mp.gw) * mp.cs - mp.hh;  // the cell's low corner
+      const double dm0 = fmax(fabs(cx - mx), fabs(cx + mp.cs - mx)) + dd, dm1 = fmax(fabs(cy - my), fabs(cy + mp.cs - my)) + dd;
+      const double l00 = H00 > 0. ? sqrt(H00) : 0.;
+      const double l10 = l00 > 0. ? H01 / l00 : 0.;
+      const double l11 = sqrt(fmax(H11 - l10 * l10, 0.));
+      // a Cholesky factor that rounding made too large would overstate A: shrink it by what sqrt/div/rounding can add
+      const double sh = 1. - 1e-12;
+      const double ez0 = 3. * u24 * (l00 * dm0 + fabs(l10) * dm1), ez1 = 3. * u24 * l11 * dm1;
+      const double hs = H00 + 2. * fabs(H01) + H11;
+      // t trades the relative loosening t*A against the absolute one kappa0/t: balanced for A of order one
+      const double kappa0 = ez0 * ez0 + ez1 * ez1 + hs * dd2;
+      const double t = fmin(fmax(sqrt(kappa0), 0x1p-10), 0x1p-3);
+      const double scale = sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634);
+      const double kappa = kappa0 / t * 1.000001;  // and the rounding of the sum it enters
+      o[0] = static_cast<float>(l00 * scale * sh);
+      o[1] = static_cast<float>(l10 * scale * sh);
+      o[2] = static_cast<float>(l11 * scale * sh);
+      o[3] = __double2float_ru(kappa * 1.4426950408889634);
+      o[4] = static_cast<float>(mx);
+      o[5] = static_cast<float>(my);
+      o[6] = o[7] = 0.f;
+    }
+    sc->rec32 = sm.rec32;
+    sc->grid = m.grid;
+    sc->x_max = static_cast<float>(mp.x_max);
+    sc->y_max = static_cast<float>(mp.y_max);
+    sc->inv_cs = static_cast<float>(mp.inv_cs);
+    sc->off_u = static_cast<float>(mp.hw * mp.inv_cs - 0.5);
+    sc->off_v = static_cast<float>(mp.hh * mp.inv_cs - 0.5);
+    sc->beta_c = prm->scr_beta_c;
+    sc->gw = mp.gw;
+    sc->base = static_cast<unsigned>(m.base) + static_cast<unsigned>(kScreenMagicBits) * (1u + static_cast<unsigned>(mp.gw));  // folds the magic bits of both coordinates
+    sc->span = m.span;
+  }
   return sm;
 }
 
@@ -670,15 +935,17 @@ __global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem
   const DevMap& mp = maps[pr.map_id];
   const Topo tp = make_topo<CL>(groups);
   SliceCtx m;
+  ScreenCtx sc;
   double2 pt[NPT];
-  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt);
+  const int screen = (CL == 1) ? prm.screen : 0;  // shared memory is laid out for it whenever the launch asks for it
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt, screen, &sc, &prm);
   if (CL > 1) cluster_barrier();  // every CTA's shared memory is carved before anyone stores into it
   double* o = out + 4 * (size_t)b;
-  int* s = stats ? stats + 2 * (size_t)b : nullptr;
+  int* s = stats ? stats + kStatsWords * (size_t)b : nullptr;
   if (mp.fast_geom)
-    sliced_body<NPT, JB, CL, true, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
+    sliced_body<NPT, JB, CL, true, kProdVariant>(m, sc, screen != 0, pt, pr, prm, sm, tp, o, s);
   else
-    sliced_body<NPT, JB, CL, false, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
+    sliced_body<NPT, JB, CL, false, kProdVariant>(m, sc, false, pt, pr, prm, sm, tp, o, s);  // the screen's geometry is the fast one
   if (threadIdx.x == 0 && tp.rank == 0) publish_result(prm.ex, b, gridDim.x / CL, o);  // the thread that wrote o
 }
 

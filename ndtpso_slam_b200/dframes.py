@@ -26,7 +26,7 @@ EXPORTS = [
     "ndtpso_dframes_config_default", "ndtpso_dframes_create", "ndtpso_dframes_destroy", "ndtpso_dframes_device_bytes",
     "ndtpso_dframes_load_laser", "ndtpso_dframes_set_scan_points", "ndtpso_dframes_update", "ndtpso_dframes_build",
     "ndtpso_dframes_align", "ndtpso_dframes_track_step", "ndtpso_dframes_download_map", "ndtpso_dframes_download_scan",
-    "ndtpso_dframes_info", "ndtpso_dframes_status", "ndtpso_dframes_kernel_times",
+    "ndtpso_dframes_info", "ndtpso_dframes_status", "ndtpso_dframes_pso_stats", "ndtpso_dframes_kernel_times",
 ]
 
 
@@ -62,6 +62,7 @@ def _lib():
         L.ndtpso_dframes_download_scan.argtypes = [vp, i32, vp, C.POINTER(i32)]
         L.ndtpso_dframes_info.argtypes = [vp, i32, vp]
         L.ndtpso_dframes_status.argtypes = [vp, vp]
+        L.ndtpso_dframes_pso_stats.argtypes = [vp, vp]
         L.ndtpso_dframes_kernel_times.argtypes = [vp, vp]
         _bound = True
     return L
@@ -176,6 +177,12 @@ class DeviceFrames:
     def status(self) -> np.ndarray:
         out = np.zeros(self.n, dtype=np.int32)
         self._check(self.L.ndtpso_dframes_status(self.h, _p(out)))
+        return out
+
+    def pso_stats(self) -> np.ndarray:
+        """[n, 4] of the last align: rounds, gbest updates, fp64 cost evaluations, evaluations settled by the fp32 screen."""
+        out = np.zeros((self.n, 4), dtype=np.int32)
+        self._check(self.L.ndtpso_dframes_pso_stats(self.h, _p(out)))
         return out
 
     def kernel_times_ms(self) -> dict:

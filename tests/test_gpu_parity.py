@@ -280,3 +280,31 @@ def test_cfg3_batch_against_oracle(oracle, ctx):
     truth = np.array([syn.trajectory_problem(syn.CFG2, b).true_pose for b in range(256)])
     err = np.abs(pose - truth)
     assert np.median(err[:, :2].max(axis=1)) < 0.02 and np.median(err[:, 2]) < 0.004
+
+
+@pytest.mark.parametrize("case,inputs", [("cfg1", "cfg1"), ("cfg2", "cfg2"), ("traj17", "traj17"), ("cfg5_0.25", "cfg5_0.25"), ("cfg5_2.0", "cfg5_2.0"),
+                                         ("edge_far_guess", "edge"), ("edge_wide_dev", "edge"), ("edge_damped", "edge"), ("np2", "np2")])
+def test_fp32_screen_changes_nothing(golden, case, inputs):
+    """The fp32 lower-bound screen (ndtpso_pso_sliced.cuh) only ever drops candidates whose fp64 cost provably fails
+    `cost < pbest` (core.cpp:94): poses AND costs are bit-identical with the screen on and off, and equal the reference."""
+    from ndtpso_slam_b200 import capi
+    c, flats = golden.problems(case, inputs)
+    flats = (flats * 150)[:150]  # more problems than SMs / 2: one CTA per problem, the form the screen runs in
+    out = {}
+    for scr in (0, 1):
+        cx = capi.Context(0)
+        cx.set_option(capi.OPT_SCREEN, scr)
+        bt = cx.batch(flats, conf_of(c))
+        bt.solve()
+        out[scr] = bt.results() + (bt.stats_ex(),)
+        bt.close()
+        cx.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2][:, :2], out[1][2][:, :2])  # same rounds, same gbest updates
+    assert (out[0][2][:, 3] == 0).all()
+    n = len(c["seeds"])
+    assert np.abs(out[1][0][:n] - c["pose"]).max() <= POSE_ATOL
+    if case in ("cfg2", "traj17"):  # (200 particles on the 0.25 m map leave no shared memory for the screen's tables)
+        assert out[1][2][:, 3].sum() > 0.5 * (out[1][2][:, 2].sum() + out[1][2][:, 3].sum())  # most evaluations are settled in fp32
+    if case == "np2":  # cell side 0.3: not the geometry the screen is written for
+        assert (out[1][2][:, 3] == 0).all()

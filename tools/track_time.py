@@ -23,4 +23,6 @@ for k in range(steps):
     pose, cost = df.track_step(scans[2 + k], s.angle_min, s.angle_increment, s.range_max, conf=conf)
 dt = (time.perf_counter() - t0) / steps * 1e3
 kt = df.kernel_times_ms()
+st = df.pso_stats()
+print("pso stats: rounds %.1f fp64 evals %.0f screened %.0f (%.1f %%)" % (st[:,0].mean(), st[:,2].mean(), st[:,3].mean(), 100*st[:,3].sum()/max(1, st[:,2].sum()+st[:,3].sum())))
 print(f"{dt:.3f} ms/step -> {B/dt*1e3:.0f} scans/s; kernels {sum(kt.values()):.3f} ms {kt}; checksum {pose.sum():.12f}")

@@ -464,7 +464,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     const ndtpso_map_view& mv = *maps[i];
     const double wc = mv.width_m / mv.cell_side, hc = mv.height_m / mv.cell_side;
     if (!(is_pow2_double(mv.cell_side) && mv.x_min == -mv.x_max && mv.y_min == -mv.y_max && wc == std::floor(wc) && hc == std::floor(hc) &&
-          mv.x_max == mv.width_m / 2. && mv.y_max == mv.height_m / 2.))
+          mv.x_max == mv.width_m / 2. && mv.y_max == mv.height_m / 2. && mv.x_max == mv.y_max))  // whole cells, square
       bt->scr_ok = false;
     bt->scr_ext = std::max(bt->scr_ext, std::max(std::fabs(mv.x_max), std::fabs(mv.y_max)));
     bt->scr_inv_cs = std::max(bt->scr_inv_cs, 1.0 / mv.cell_side);

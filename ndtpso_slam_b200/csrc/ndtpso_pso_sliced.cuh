@@ -319,10 +319,11 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //     results flushed to zero:  L = -(sum (1 + 2^-14)) - 1e-6.
 // cost >= L because each fp64 term is >= -(upper bound of its exponential).
 struct ScreenCtx {
-  const float* rec32;          // shared: [n_rec + 1][8] = {l00, l10, l11, kappa2, mx, my, -, -}
+  const float* rec32;          // shared: [n_rec + 1][8] = {l00, l11, l10, kappa2, -mx, -my, -, -}
   const unsigned short* grid;  // shared
-  float x_max, y_max, inv_cs, off_u, off_v;  // off = (W/2)/cs - 0.5: the cell coordinate minus one half
-  float beta_c;                              // 0.5 - beta
+  float2 k2, off2;  // (1/cs, 1/cs) and ((W/2)/cs - 0.5, (H/2)/cs - 0.5): the cell coordinates minus one half
+  float x_max;      // square frames: x_max == y_max
+  float beta_c;     // 0.5 - beta
   int gw, span;
   unsigned base;
 };
@@ -330,25 +331,29 @@ struct ScreenCtx {
 constexpr float kScreenMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to an integer
 constexpr int kScreenMagicBits = 0x4B400000;     // its bit pattern
 
-__device__ __forceinline__ void screen_point(const ScreenCtx& m, const float2 p, const float4 ps, float& acc) {
-  const float x = fmaf(p.x, ps.z, fmaf(-p.y, ps.w, ps.x));
-  const float y = fmaf(p.x, ps.w, fmaf(p.y, ps.z, ps.y));
-  const bool inb = (fabsf(x) < m.x_max) && (fabsf(y) < m.y_max);  // only trusted away from the cell edges
-  const float uh = fmaf(x, m.inv_cs, m.off_u), vh = fmaf(y, m.inv_cs, m.off_v);  // cell coordinate - 0.5
-  const float tu = uh + kScreenMagic, tv = vh + kScreenMagic;  // round to nearest of (u - 0.5) = floor(u), for |u| < 2^22
-  // distance of the fractional part from 0.5: beyond 0.5 - beta means within beta of an edge
-  const bool unc = (fabsf(uh - (tu - kScreenMagic)) > m.beta_c) || (fabsf(vh - (tv - kScreenMagic)) > m.beta_c);
-  // ix + gw*iy - base with ix = bits(tu) - magic bits: the constants are folded into `base`
-  const unsigned g = __float_as_uint(tu) + static_cast<unsigned>(m.gw) * __float_as_uint(tv) - m.base;  // wraps like the folded constants
-  const bool in_strip = inb && (g < static_cast<unsigned>(m.span));
-  const unsigned r = m.grid[in_strip ? g : static_cast<unsigned>(m.span)];
+// One scan point against one candidate, with Blackwell's packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2: two IEEE results per
+// instruction) wherever x and y go through the same operation — the loop is bound by instruction issue, not by the fp32 pipe.
+//   px2 = (px, px), py2 = (py, py);  cs = (cos, sin), sc = (-sin, cos), txy = (tx, ty) of the candidate
+__device__ __forceinline__ void screen_point(const ScreenCtx& m, const float2 px2, const float2 py2, const float2 txy, const float2 cs,
+                                             const float2 sc, float& acc) {
+  const float2 xy = __ffma2_rn(px2, cs, __ffma2_rn(py2, sc, txy));  // transform_point
+  const bool inb = fmaxf(fabsf(xy.x), fabsf(xy.y)) < m.x_max;       // square frames only; trusted away from the cell edges
+  const float2 uv = __ffma2_rn(xy, m.k2, m.off2);                   // cell coordinates - 0.5
+  const float2 t2 = __fadd2_rn(uv, make_float2(kScreenMagic, kScreenMagic));  // round to nearest of (u - 0.5) = floor(u), |u| < 2^22
+  const float2 fl = __fadd2_rn(t2, make_float2(-kScreenMagic, -kScreenMagic));
+  const float2 df = __ffma2_rn(fl, make_float2(-1.f, -1.f), uv);    // fractional part - 0.5
+  const bool unc = fmaxf(fabsf(df.x), fabsf(df.y)) > m.beta_c;      // within beta of a cell edge
+  // ix + gw*iy - base with ix = bits(t) - magic bits: the constants are folded into `base`
+  const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y) - m.base;
+  const unsigned gs = inb ? min(g, static_cast<unsigned>(m.span)) : static_cast<unsigned>(m.span);
+  const unsigned r = m.grid[gs];
   const float* q = m.rec32 + 8 * r;
-  const float4 l = *reinterpret_cast<const float4*>(q);  // l00, l10, l11, kappa2
-  const float2 mu = *reinterpret_cast<const float2*>(q + 4);
-  const float d0 = x - mu.x, d1 = y - mu.y;
-  const float z0 = fmaf(l.y, d1, l.x * d0);
-  const float z1 = l.z * d1;
-  const float xe = fmaf(-z1, z1, fmaf(-z0, z0, l.w));
+  const float4 l = *reinterpret_cast<const float4*>(q);        // l00, l11, l10, kappa2
+  const float2 nmu = *reinterpret_cast<const float2*>(q + 4);  // -mx, -my
+  const float2 d = __fadd2_rn(xy, nmu);
+  const float2 zz = __fmul2_rn(make_float2(l.x, l.y), d);      // l00 d0, l11 d1
+  const float z0 = fmaf(l.z, d.y, zz.x);
+  const float xe = fmaf(-zz.y, zz.y, fmaf(-z0, z0, l.w));
   float e;  // ex2.approx: 2 ulp, results below 2^-126 flushed to zero; both covered by the total's slack
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(xe, 0.f)));
   acc += unc ? 1.0f : e;
@@ -382,8 +387,8 @@ __device__ __forceinline__ float packed_warp_sum_f<4>(const float (&a)[4], int l
 
 // screen of candidates j .. j+JB-1 (clamped to hi-1) on this warp's slice: lbpart[j*NW + warp] = sum of the upper bounds
 template <int NPT, int JB>
-__device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&pf)[NPT], const float4* pose32, float* lbpart, int j, int hi,
-                                             int NW, int warp, int lane) {
+__device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&px2)[NPT], const float2 (&py2)[NPT], const float4* pose32,
+                                             float* lbpart, int j, int hi, int NW, int warp, int lane) {
   float acc[JB];
   float4 ps[JB];
 #pragma unroll
@@ -393,8 +398,9 @@ __device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&
   }
 #pragma unroll
   for (int b = 0; b < JB; ++b) {
+    const float2 txy = make_float2(ps[b].x, ps[b].y), cs = make_float2(ps[b].z, ps[b].w), sc = make_float2(-ps[b].w, ps[b].z);
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) screen_point(m, pf[k], ps[b], acc[b]);
+    for (int k = 0; k < NPT; ++k) screen_point(m, px2[k], py2[k], txy, cs, sc, acc[b]);
   }
   const float tot = packed_warp_sum_f<JB>(acc, lane);
   const int jj = j + packed_slot<JB>(lane);
@@ -642,14 +648,17 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
     if (start == 0) prefetch_draws(it + 1);  // first round of an iteration
     if (CL == 1 && FAST_GEOM && scr) {
       // phase B1: fp32 lower bound of every pending candidate's cost on this warp's slice
-      float2 pf[NPT];
+      float2 px2[NPT], py2[NPT];
 #pragma unroll
-      for (int k = 0; k < NPT; ++k)  // padding points (1e200, 0) become (1e30, 0): still outside every frame, but finite in fp32
-        pf[k] = make_float2(static_cast<float>(fmin(pt[k].x, 1e30)), static_cast<float>(pt[k].y));
+      for (int k = 0; k < NPT; ++k) {  // padding points (1e200, 0) become (1e30, 0): still outside every frame, but finite in fp32
+        const float fx = static_cast<float>(fmin(pt[k].x, 1e30)), fy = static_cast<float>(pt[k].y);
+        px2[k] = make_float2(fx, fx);
+        py2[k] = make_float2(fy, fy);
+      }
       {
         int j = start;
-        for (; j + 4 <= lim; j += 4) screen_batch<NPT, 4>(sc, pf, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
-        for (; j < lim; j += 2) screen_batch<NPT, 2>(sc, pf, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
+        for (; j + 4 <= lim; j += 4) screen_batch<NPT, 4>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
+        for (; j < lim; j += 2) screen_batch<NPT, 2>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
       }
       __syncthreads();
       // warp 0 lists the candidates whose bound does not already rule out an improvement of their particle's best
@@ -888,20 +897,18 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
       const double scale = sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634);
       const double kappa = kappa0 / t * 1.000001;  // and the rounding of the sum it enters
       o[0] = static_cast<float>(l00 * scale * sh);
-      o[1] = static_cast<float>(l10 * scale * sh);
-      o[2] = static_cast<float>(l11 * scale * sh);
+      o[1] = static_cast<float>(l11 * scale * sh);
+      o[2] = static_cast<float>(l10 * scale * sh);
       o[3] = __double2float_ru(kappa * 1.4426950408889634);
-      o[4] = static_cast<float>(mx);
-      o[5] = static_cast<float>(my);
+      o[4] = -static_cast<float>(mx);
+      o[5] = -static_cast<float>(my);
       o[6] = o[7] = 0.f;
     }
     sc->rec32 = sm.rec32;
     sc->grid = m.grid;
     sc->x_max = static_cast<float>(mp.x_max);
-    sc->y_max = static_cast<float>(mp.y_max);
-    sc->inv_cs = static_cast<float>(mp.inv_cs);
-    sc->off_u = static_cast<float>(mp.hw * mp.inv_cs - 0.5);
-    sc->off_v = static_cast<float>(mp.hh * mp.inv_cs - 0.5);
+    sc->k2 = make_float2(static_cast<float>(mp.inv_cs), static_cast<float>(mp.inv_cs));
+    sc->off2 = make_float2(static_cast<float>(mp.hw * mp.inv_cs - 0.5), static_cast<float>(mp.hh * mp.inv_cs - 0.5));
     sc->beta_c = prm->scr_beta_c;
     sc->gw = mp.gw;
     sc->base = static_cast<unsigned>(m.base) + static_cast<unsigned>(kScreenMagicBits) * (1u + static_cast<unsigned>(mp.gw));  // folds the magic bits of both coordinates

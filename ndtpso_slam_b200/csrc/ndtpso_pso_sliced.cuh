@@ -692,7 +692,8 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
       {
         int i = 0;
         for (; i + 4 <= ns; i += 4) score_batch_listed<NPT, 4, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
-        for (; i < ns; i += 2) score_batch_listed<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
+        for (; i + 2 <= ns; i += 2) score_batch_listed<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
+        if (i < ns) score_batch_listed<NPT, 1, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);  // survivors are few: no padding
       }
     } else {
       n_f64 += lim - start;

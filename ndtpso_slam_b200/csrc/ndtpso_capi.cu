@@ -35,7 +35,7 @@ struct PoolBuf {
 };
 
 constexpr size_t kAlign = 256;
-constexpr int kDefaultHotChunk = 12;  // speculation window of the sliced kernel while gbest improves often (tools/chunk_sweep.py)
+constexpr int kDefaultHotChunk = 16;  // speculation window of the sliced kernel while gbest improves often (tools/chunk_sweep.py)
 inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
 
 }  // namespace

@@ -308,3 +308,45 @@ def test_fp32_screen_changes_nothing(golden, case, inputs):
         assert out[1][2][:, 3].sum() > 0.5 * (out[1][2][:, 2].sum() + out[1][2][:, 3].sum())  # most evaluations are settled in fp32
     if case == "np2":  # cell side 0.3: not the geometry the screen is written for
         assert (out[1][2][:, 3] == 0).all()
+
+
+def test_fp32_screen_on_random_tables(oracle):
+    """Random maps with sharp, strongly correlated Sigma^-1 (up to 1e6, correlation up to 0.999), means anywhere in their
+    cells, scans with points on cell edges and on the frame's border: screen on == screen off bit for bit, == oracle."""
+    rng = np.random.default_rng(5)
+    gw = gh = 40
+    n = gw * gh
+    flats = []
+    for m_id in range(3):
+        built = (rng.random(n) < 0.3).astype(np.uint8)
+        ix, iy = np.arange(n) % gw, np.arange(n) // gw
+        mean = np.stack([(ix + rng.random(n)) * 0.5 - 10.0, (iy + rng.random(n)) * 0.5 - 10.0], 1)
+        scale = 10.0 ** rng.uniform(0.5, 6.0, n)
+        a, b = scale * rng.uniform(0.2, 1.0, n), scale * rng.uniform(0.2, 1.0, n)
+        r = rng.choice([0.0, 0.5, 0.99, 0.999], n) * rng.choice([-1.0, 1.0], n) * np.sqrt(a * b)
+        icov = np.stack([a, r, r, b], 1)
+        pts = rng.uniform(-9.5, 9.5, size=(900, 2))
+        pts[:60] = np.round(pts[:60] * 2) / 2          # exactly on cell edges
+        pts[60:80, 0] = 10.0 - 1e-9 * rng.random(20)   # a hair inside the frame's border
+        flat = dict(points=pts, mean=mean, inv_cov=icov, built=built, w_cells=gw, h_cells=gh, width_m=20.0, height_m=20.0,
+                    cell_side=0.5, x_min=-10.0, x_max=10.0, y_min=-10.0, y_max=10.0)
+        for s in range(50):
+            f = dict(flat)
+            f.update(guess=(0.0, 0.0, 0.0) if s % 2 else (0.25, -0.5, 0.3), deviation=(0.3, 0.3, 0.05), seed=1 + 50 * m_id + s)
+            flats.append(f)
+    conf = capi.PsoConfig.make(population=40, iterations=15)
+    out = {}
+    for scr in (0, 1):
+        cx = capi.Context(0)
+        cx.set_option(capi.OPT_SCREEN, scr)
+        bt = cx.batch(flats, conf)
+        bt.solve()
+        out[scr] = bt.results() + (bt.stats_ex(),)
+        bt.close()
+        cx.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[1][2][:, 3].sum() > 0  # the screen did run
+    for i in (0, 57, 101, 149):
+        po, co, _ = oracle.pso(flats[i], flats[i]["guess"], flats[i]["deviation"], 40, 15, seed=flats[i]["seed"])
+        assert np.abs(out[1][0][i] - po).max() <= POSE_ATOL
+        assert rel_err(out[1][1][i], co) <= SCORE_RTOL

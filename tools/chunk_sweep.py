@@ -6,7 +6,7 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 flats = workload.cfg2_batch(batch)
 conf = capi.PsoConfig.make(population=70, iterations=50)
 ref = None
-for chunk, th in ((0, 1), (8, 1), (12, 1), (16, 1), (8, 2), (12, 2), (4, 1), (0, 1)):
+for chunk, th in ((0, 1), (12, 1), (16, 1), (24, 1), (32, 1), (24, 2), (16, 2), (12, 1)):
     ctx = capi.Context(0)
     ctx.set_option(capi.OPT_HOT_CHUNK, chunk | (th << 16))
     bt = ctx.batch(flats, conf)

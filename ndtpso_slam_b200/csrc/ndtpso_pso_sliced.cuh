@@ -534,6 +534,13 @@ __device__ __forceinline__ double candidate_total(const double* part, int j, int
   return (c0 + c1) + (c2 + c3);
 }
 
+// candidate_total, or the +1e300 the screen left in the first partial of a candidate it ruled out (the other partials of
+// such a candidate are stale)
+__device__ __forceinline__ double candidate_cost(const double* part, int j, int PW) {
+  const double p0 = part[j * PW];
+  return p0 > 1e299 ? p0 : candidate_total(part, j, PW);
+}
+
 template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
 __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& sc, const bool scr, const double2 (&pt)[NPT],
                                             const DevProblem& pr, const PsoParams& prm, const SlicedSmem& sm, const Topo& tp,
@@ -661,6 +668,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
         for (; j < lim; j += 2) screen_batch<NPT, 2>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
       }
       __syncthreads();
+      NDTPSO_PHASE_MARK(5)
       // warp 0 lists the candidates whose bound does not already rule out an improvement of their particle's best
       // (core.cpp:94); the others get a cost of +1e300, which phase C treats like any cost that improves nothing
       if (warp == 0) {
@@ -670,13 +678,23 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
           bool alive = false;
           if (j < lim) {
             double u = 0.;
-            for (int w2 = 0; w2 < tp.NW; ++w2) u += static_cast<double>(sm.lbpart[j * tp.NW + w2]);
+            if ((tp.NW & 3) == 0) {  // rows of 16-byte multiples: vector loads, four independent sums
+              const float4* row = reinterpret_cast<const float4*>(sm.lbpart + j * tp.NW);
+              double u0 = 0., u1 = 0., u2 = 0., u3 = 0.;
+              for (int w2 = 0; w2 < tp.NW / 4; ++w2) {
+                const float4 q = row[w2];
+                u0 += static_cast<double>(q.x);
+                u1 += static_cast<double>(q.y);
+                u2 += static_cast<double>(q.z);
+                u3 += static_cast<double>(q.w);
+              }
+              u = (u0 + u1) + (u2 + u3);
+            } else {
+              for (int w2 = 0; w2 < tp.NW; ++w2) u += static_cast<double>(sm.lbpart[j * tp.NW + w2]);
+            }
             const double lower = -(u * (1. + 6.103515625e-5)) - 1e-6;  // slack: ex2.approx, fp32 products and sums (2^-14), flushed denormals
             alive = !(lower >= sm.pbc[j]);
-            if (!alive) {
-              part[j * PW] = 1e300;
-              for (int w2 = 1; w2 < PW; ++w2) part[j * PW + w2] = 0.;
-            }
+            if (!alive) part[j * PW] = 1e300;  // candidate_cost() looks at this entry first
           }
           const unsigned mask = __ballot_sync(0xffffffffu, alive);
           if (alive) sm.surv[ns + __popc(mask & ((1u << lane) - 1u))] = j;
@@ -685,6 +703,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
         if (lane == 0) sm.surv[P + 1] = ns;
       }
       __syncthreads();
+      NDTPSO_PHASE_MARK(6)
       // phase B2: the fp64 evaluation of the survivors
       const int ns = sm.surv[P + 1];
       n_f64 += ns;
@@ -710,7 +729,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
     double cstar = 0.;
     for (int base = start; base < lim && jstar < 0; base += 32) {
       const int j = base + lane;
-      const double cj = (j < lim) ? candidate_total(part, j, PW) : 0.;
+      const double cj = (j < lim) ? candidate_cost(part, j, PW) : 0.;
       const bool imp = (j < lim) && (cj < gbc);
       const unsigned mask = __ballot_sync(0xffffffffu, imp);
       if (mask) {
@@ -722,7 +741,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
     const int end = (jstar >= 0) ? jstar + 1 : lim;
     for (int j = ja; j < end; j += T) {  // commit own particles in [start, end)  (core.cpp:89-96)
       const Pose ps = pose[j];
-      const double cj = candidate_total(part, j, PW);
+      const double cj = candidate_cost(part, j, PW);
       sm.x[3 * j] = ps.x;
       sm.x[3 * j + 1] = ps.y;
       sm.x[3 * j + 2] = ps.th;

@@ -15,8 +15,8 @@ L.ndtpso_bench_phase_cycles(None, 1)
 bt.solve(); bt.results()
 out = (C.c_ulonglong * 8)()
 L.ndtpso_bench_phase_cycles(out, 0)
-v = list(out)[:5]; tot = sum(v)
-names = ["prologue+init", "phase A + barrier", "phase B (own scoring)", "barrier after B", "phase C"]
+v = list(out)[:7]; tot = sum(v)
+names = ["prologue+init", "phase A + barrier", "phase B2 (fp64 scoring of the survivors; all of B without the screen)", "barrier after B", "phase C", "phase B1 (fp32 screen) + barrier", "survivor list + barrier"]
 print(f"B={batch}: kernel {bt.kernel_times_ms()[2]:.3f} ms; per-CTA mean cycles {tot / batch:.0f}")
 for n, x in zip(names, v):
     print(f"  {n:24s} {x / batch:12.0f} cycles/CTA  {x / tot:6.1%}")

@@ -526,7 +526,7 @@ def _run_gpu_arm(args, real_stdout):
                                       "fp64_tflops": ALG_FLOP_PER_MATCH * B / k2_iso_s / 1e12,
                                       "note": "one launch alone on the GPU (single stream): 256 CTAs fill 86 % of the 296 CTA slots"},
                          "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                                  "note": "algorithmic flops (31/point-eval); peak = DFMA probe on this GPU; this is the bound that binds"}},
+                                  "note": "algorithmic flops (31 per point-evaluation x the 3571 cost evaluations a match makes in the reference); peak = DFMA probe on this GPU. The fp32 screen settles ~86 % of those evaluations without touching the fp64 pipe, so this is work delivered per second, not pipe utilisation (ncu: profiles/)"}},
             "single_stream": {"value": world * B * n_single / (single_ms * 1e-3), "unit": "scan-matches/s", "ms_per_step": single_ms / n_single,
                               "note": "one resident batch, one stream, L2 flushed (256 MiB write) between steps, per-step CUDA events"},
             "single_match": single,

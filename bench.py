@@ -328,18 +328,19 @@ def _run_gpu_arm(args, real_stdout):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident arm: value.  Two resident copies of the batch alternate on two streams (step k -> copy k & 1): a
+    # ---- resident arm: value.  Resident copies of the batch alternate on two streams (step k -> copy k % 4, stream k & 1): a
     # batch of 256 CTAs leaves 40 of the 296 CTA slots empty and drains unevenly, and with the next step on the other
     # stream its CTAs take the free slots at once.  Every step is a full pass of the hot path over one batch (K0 table
-    # compaction, K1 rand() streams, K2 PSO, result exchange for N > 1); inputs are 2 x 130 MB > L2, so a step never
-    # finds its tables in cache.  The single-stream, L2-flushed form is measured beside it (`single_stream`), and the
+    # compaction, K1 rand() streams, K2 PSO, result exchange for N > 1); four copies are cycled so that what a step
+    # touches (~41 MB) has been pushed out of the 126 MB L2 by the three steps in between.  The single-stream, L2-flushed form is measured beside it (`single_stream`), and the
     # roofline uses that form's kernel durations.
+    NCOPY = 4  # resident copies of the batch, used round-robin: 4 x ~41 MB touched per step (compact tables, rand streams, flags) > 126 MB of L2
     streams = [stream, torch.cuda.Stream()]
-    bts = [ctx.batch(pset, conf), ctx.batch(pset, conf)]
+    bts = [ctx.batch(pset, conf) for _ in range(NCOPY)]
     bt = bts[0]
-    res_ts = [None, None]
+    res_ts = [None] * NCOPY
     if world > 1:
-        for i in range(2):
+        for i in range(NCOPY):
             # view the library's result buffer as a tensor for the NCCL all-gather of the solved poses
             class _Ext:
                 __cuda_array_interface__ = {"shape": (B * 4,), "typestr": "<f8", "data": (bts[i].device_results_ptr(), False), "version": 3}
@@ -349,13 +350,13 @@ def _run_gpu_arm(args, real_stdout):
     # stores each result into every rank's gathered buffer over NVLink (CUDA IPC) and ndtpso_exchange_wait polls the
     # arrival flags — no collective per step.  NCCL's all-gather is the reference implementation: used to verify the
     # fused form once, and as the per-step exchange if CUDA IPC is unavailable (--exchange nccl forces it).
-    exs, exchange_kind = [None, None], "none"
+    exs, exchange_kind = [None] * NCOPY, "none"
     if world > 1:
         exchange_kind = "NCCL all-gather of [B][4] fp64 poses per step"
         if args.exchange == "fused":
-            exs = [sharding.make_exchange(ctx, B, world, rank, device="cuda") for _ in range(2)]  # None on every rank if IPC fails anywhere
-            if exs[0] is not None and exs[1] is not None:
-                for i in range(2):
+            exs = [sharding.make_exchange(ctx, B, world, rank, device="cuda") for _ in range(NCOPY)]  # None on every rank if IPC fails anywhere
+            if all(e_ is not None for e_ in exs):
+                for i in range(NCOPY):
                     bts[i].attach_exchange(exs[i])
                 exchange_kind = ("peer stores of the [B][4] fp64 poses from the PSO kernel's epilogue into every rank's gathered buffer "
                                  "(NVLink, CUDA IPC) + arrival-flag wait kernel; verified against an NCCL all-gather")
@@ -364,16 +365,17 @@ def _run_gpu_arm(args, real_stdout):
                 for e_ in exs:
                     if e_ is not None:
                         e_.close()
-                exs = [None, None]
+                exs = [None] * NCOPY
     ex = exs[0]
 
     def resident_step(i=0):
-        ctx.set_stream(streams[i].cuda_stream)
+        st = streams[i & 1]
+        ctx.set_stream(st.cuda_stream)
         bts[i].solve()
         if exs[i] is not None:
             exs[i].wait()
         elif world > 1:
-            with torch.cuda.stream(streams[i]):
+            with torch.cuda.stream(st):
                 sharding.gather_results(res_ts[i].view(B, 4), world * B, world, rank)
 
     if ex is not None:  # once: the fused exchange delivers exactly what the collective delivers
@@ -403,8 +405,8 @@ def _run_gpu_arm(args, real_stdout):
     kt = bts[0].kernel_times_ms()  # last solve: K0, K1, K2, not overlapped with anything
 
     # the timed region: K steps alternating between the two copies / streams
-    for k in range(args.warmup):
-        resident_step(k & 1)
+    for k in range(max(args.warmup, NCOPY)):
+        resident_step(k % NCOPY)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -413,7 +415,7 @@ def _run_gpu_arm(args, real_stdout):
     barrier()
     ev_start.record(streams[0])
     for k in range(args.steps):
-        resident_step(k & 1)
+        resident_step(k % NCOPY)
     streams[0].wait_stream(streams[1])
     ev_end.record(streams[0])
     barrier()
@@ -425,8 +427,9 @@ def _run_gpu_arm(args, real_stdout):
         total_ms, single_ms = float(t[0].item()), float(t[1].item())
     ctx.set_stream(streams[0].cuda_stream)
     pose, cost = bts[0].results()
-    pose1, cost1 = bts[1].results()
-    assert np.array_equal(pose, pose1) and np.array_equal(cost, cost1), "the two resident copies disagree"
+    for i in range(1, NCOPY):
+        pose1, cost1 = bts[i].results()
+        assert np.array_equal(pose, pose1) and np.array_equal(cost, cost1), "the resident copies disagree"
     stats = bts[0].stats()
 
     # ---- e2e arm: host buffers in, host poses out, every step.  Throughput form of the public API:
@@ -463,7 +466,7 @@ def _run_gpu_arm(args, real_stdout):
     assert np.array_equal(ep, pose), "e2e and resident paths disagree"
 
     fp64_peak = ctx.fp64_peak_tflops()
-    for i in range(2):
+    for i in range(NCOPY):
         if exs[i] is not None:
             bts[i].attach_exchange(None)
         bts[i].close()
@@ -510,8 +513,9 @@ def _run_gpu_arm(args, real_stdout):
             "config": {"workload": f"cfg2 shape (configs[1]; batched as configs[2]): {B} independent 1081-beam scan-matches per GPU vs "
                                    "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations",
                        "batch_per_gpu": B, "particles": P, "iterations": I,
-                       "l2": "inputs larger than L2: two resident copies of the batch (2 x 130 MB of tables) alternate step by step",
-                       "pipelining": "step k runs on stream k & 1 (two resident copies), so consecutive steps overlap while one drains",
+                       "l2": "inputs larger than L2: four resident copies of the batch (4 x 130 MB of dense tables, of which a step touches ~41 MB: "
+                             "built flags, built cells, compact tables, rand streams) are used round-robin, 164 MB between two uses of a copy",
+                       "pipelining": "step k runs on copy k % 4 and stream k & 1, so consecutive steps overlap while one drains",
                        "collective": exchange_kind},
             "e2e": {"value": e2e, "unit": "scan-matches/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "api": "ndtpso_align_submit/collect, 2 batches in flight",

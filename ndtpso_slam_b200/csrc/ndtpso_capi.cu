@@ -560,11 +560,12 @@ int launch_pso(ndtpso_batch* bt, int smem) {
 // launch_sliced returns 1 when the batch does not qualify (table too large for shared memory,
 // scan too long, > 65534 built cells, asymmetric Sigma^-1).
 // Constants of the fp32 screen's error bound for this batch (see ndtpso_pso_sliced.cuh); false = the batch does not qualify.
-//   dx: error of a transformed point's coordinate in fp32.  For a point that ends up inside a frame, |t| <= ext + 2 pmax, so
-//       inputs (p, cos, sin, t rounded to fp32: 2^-24 relative each) and the two FMAs give at most 2^-24 (6 pmax + 3 ext);
-//       taken as 2^-23 (8 pmax + 4 ext).
-//   dd: error of its offset from a cell mean: dx + rounding of the mean and of the subtraction; doubled for safety.
-//   beta: band around cell edges inside which fp32 and fp64 may pick different cells: 8x the error of the cell coordinate.
+//   dx: error of a transformed point's coordinate in fp32, x = fma(px, c, fma(-py, s, tx)) with every input rounded to fp32
+//       (u = 2^-24 relative each): to first order u (3|px c| + 4|py s| + 3|tx| + |x|).  For a point that ends up inside a frame
+//       |x| <= ext and |tx| <= ext + 1.42 pmax, so dx <= u (11.3 pmax + 4 ext) = 2^-23 (5.7 pmax + 2 ext); taken as
+//       2^-23 (8 pmax + 4 ext).
+//   dd: error of its offset from a cell mean: dx + rounding of the mean and of the subtraction (<= 2^-23 ext), times 1.25.
+//   beta: band around cell edges inside which fp32 and fp64 may pick different cells: 4x the error of the cell coordinate.
 bool screen_params(const ndtpso_batch* bt, PsoParams* prm) {
   prm->screen = 0;
   const ndtpso_ctx* ctx = bt->ctx;
@@ -572,9 +573,9 @@ bool screen_params(const ndtpso_batch* bt, PsoParams* prm) {
   const double u23 = 1.1920928955078125e-07;  // 2^-23
   const double pmax = std::max(bt->scr_pmax, 1.0), ext = bt->scr_ext;
   const double dx = u23 * (8. * pmax + 4. * ext);
-  const double dd = 2. * (dx + u23 * ext);
+  const double dd = 1.25 * (dx + u23 * ext);
   const double du = dx * bt->scr_inv_cs + u23 * bt->scr_gw;
-  const double beta = std::max(1e-3, 8. * du);
+  const double beta = std::max(5e-4, 4. * du);
   if (beta > 0.05) return false;
   prm->screen = 1;
   prm->scr_dd2 = (float)(dd * dd * 1.000001);

@@ -31,6 +31,9 @@ enum {
   VAR_PIN_CONSTS = 4,     // keep 16/ln2 and 1/7! in vector registers (loaded through a lane-dependent address) instead of
                           // re-materialising them from uniform registers with two moves per use: -4 instructions per evaluation
 };
+#ifndef NDTPSO_SCREEN_JB8
+#define NDTPSO_SCREEN_JB8 1  // the screen takes candidates eight at a time first (more loads in flight, fewer reductions): +2 %
+#endif
 #ifndef NDTPSO_PROD_VARIANT
 #define NDTPSO_PROD_VARIANT 4
 #endif
@@ -385,6 +388,28 @@ __device__ __forceinline__ float packed_warp_sum_f<4>(const float (&a)[4], int l
   return k;
 }
 
+template <>
+__device__ __forceinline__ float packed_warp_sum_f<8>(const float (&a)[8], int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0, hi4 = (lane & 4) != 0;
+  float k01 = hi16 ? a[1] : a[0];
+  k01 += __shfl_xor_sync(0xffffffffu, hi16 ? a[0] : a[1], 16);
+  float k23 = hi16 ? a[3] : a[2];
+  k23 += __shfl_xor_sync(0xffffffffu, hi16 ? a[2] : a[3], 16);
+  float k45 = hi16 ? a[5] : a[4];
+  k45 += __shfl_xor_sync(0xffffffffu, hi16 ? a[4] : a[5], 16);
+  float k67 = hi16 ? a[7] : a[6];
+  k67 += __shfl_xor_sync(0xffffffffu, hi16 ? a[6] : a[7], 16);
+  float ka = hi8 ? k23 : k01;
+  ka += __shfl_xor_sync(0xffffffffu, hi8 ? k01 : k23, 8);
+  float kb = hi8 ? k67 : k45;
+  kb += __shfl_xor_sync(0xffffffffu, hi8 ? k45 : k67, 8);
+  float k = hi4 ? kb : ka;
+  k += __shfl_xor_sync(0xffffffffu, hi4 ? ka : kb, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
 // screen of candidates j .. j+JB-1 (clamped to hi-1) on this warp's slice: lbpart[j*NW + warp] = sum of the upper bounds
 template <int NPT, int JB>
 __device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&px2)[NPT], const float2 (&py2)[NPT], const float4* pose32,
@@ -664,6 +689,9 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
       }
       {
         int j = start;
+#if NDTPSO_SCREEN_JB8
+        for (; j + 8 <= lim; j += 8) screen_batch<NPT, 8>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
+#endif
         for (; j + 4 <= lim; j += 4) screen_batch<NPT, 4>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
         for (; j < lim; j += 2) screen_batch<NPT, 2>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
       }

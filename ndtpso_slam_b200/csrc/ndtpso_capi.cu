@@ -102,6 +102,7 @@ struct ndtpso_batch {
   int need_dyn_smem = 0;  // points + records + grid of the largest problem
   int max_pts = 0;        // largest scan
   int max_table_smem = 0; // records + grid of the largest table
+  int max_n_rec = 0;      // built cells of the largest table
   bool all_compact = true;  // every table has <= 65534 built cells
   bool all_symmetric = true;  // every built cell: S01 == S10 bit for bit, finite, positive semi-definite (NDTCell::build always does)
   bool solved = false;
@@ -470,6 +471,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     bt->scr_inv_cs = std::max(bt->scr_inv_cs, 1.0 / mv.cell_side);
     bt->scr_gw = std::max(bt->scr_gw, std::max(mv.w_cells, mv.h_cells));
     bt->max_table_smem = std::max(bt->max_table_smem, map_dyn[i]);
+    bt->max_n_rec = std::max(bt->max_n_rec, scans[i].n_rec);
     if (scans[i].n_rec > 65534) bt->all_compact = false;
     if (!scans[i].symmetric) bt->all_symmetric = false;
   }
@@ -709,9 +711,9 @@ int launch_sliced(ndtpso_batch* bt) {
   if (npt < 1 || npt > kSlicedMaxNPT || nw > kSlicedMaxWarps[npt]) return 1;
   nw = std::max(nw, 4);
   PsoParams probe{};
-  bool scr = npt == 3 && (ctx->opt_cand_batch == 0 || ctx->opt_cand_batch == 4) && screen_params(bt, &probe);  // the default shape only
+  bool scr = screen_params(bt, &probe);
   const int smem_plain = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, 0));
-  int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, scr ? 1 : 0));
+  int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, scr ? bt->max_n_rec + 1 : 0));
   // not at the price of the second CTA per SM, and not beyond what a CTA may have
   if (scr && (smem > ctx->max_smem_optin || (smem > ctx->max_smem_optin / 2 && smem_plain <= ctx->max_smem_optin / 2))) {
     scr = false;
@@ -720,15 +722,15 @@ int launch_sliced(ndtpso_batch* bt) {
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;
   switch (npt) {
-    case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 1, 640, 1>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<1, 2, 1, 640, 1>(bt, nw, 1, smem)
-                                                                                        : launch_sliced_cfg<1, 4, 1, 640, 1>(bt, nw, 1, smem);
-    case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 1, 640, 1>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<2, 2, 1, 640, 1>(bt, nw, 1, smem)
-                                                                                        : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem);
-    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem)
+    case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 1, 640, 1>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<1, 2, 1, 640, 1>(bt, nw, 1, smem, scr)
+                                                                                        : launch_sliced_cfg<1, 4, 1, 640, 1>(bt, nw, 1, smem, scr);
+    case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 1, 640, 1>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<2, 2, 1, 640, 1>(bt, nw, 1, smem, scr)
+                                                                                        : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem, scr);
+    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem, scr)
                                                                                         : launch_sliced_cfg<3, 4, 1, 384, 2>(bt, nw, 1, smem, scr);
-    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem);
-    case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem);
-    default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem);
+    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem, scr);
+    case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
+    default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
   }
 }
 

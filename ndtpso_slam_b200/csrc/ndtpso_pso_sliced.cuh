@@ -9,7 +9,9 @@
 //   -- barrier --
 //   B  every warp evaluates EVERY pending candidate on its own slice of the scan, JB candidates at
 //      a time (branch-free NDT score, fast_exp, JB*NPT independent evaluations in flight per lane),
-//      packed warp-shuffle reduction -> partial[j][warp]
+//      packed warp-shuffle reduction -> partial[j][warp].  With the fp32 screen (one CTA per problem,
+//      see "fp32 screen" below) B is B1, a rigorous fp32 lower bound of every pending candidate's
+//      cost, then B2, the fp64 evaluation of only those candidates the bound does not rule out.
 //   -- barrier --
 //   C  every warp sums the partials of the pending candidates (fixed order), finds j* = the first
 //      candidate that beats gbest (ballot), owners commit particles <= j* (core.cpp:89-105);
@@ -104,11 +106,11 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
 __host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
   return (P + 1) * 16 + round16((P + 1) * NW * 4) + round16((P + 2) * 4);
 }
-// total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2).  With the screen the fp32 records take
-// (n_rec + 1) * 32 bytes more, at most two thirds of table_bytes.
-__host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int table_bytes, int screen = 0) {
+// total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2).  With the screen (screen_recs > 0:
+// the largest record count of the batch, null record included) the fp32 records take screen_recs * 32 bytes more.
+__host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int table_bytes, int screen_recs = 0) {
   return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP) +
-         (screen ? sliced_screen_fixed_bytes(P, PW) + round16(table_bytes * 2 / 3 + 16) : 0);
+         (screen_recs > 0 ? sliced_screen_fixed_bytes(P, PW) + round16(screen_recs * 32) : 0);
 }
 
 __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int PW, int WP, int table_bytes, int screen = 0) {

@@ -328,3 +328,32 @@ def test_points_outside_the_map_are_dropped_like_the_reference(ctx, reference):
         _assert_tables_equal(df.download_map(0), ref.flatten_map(), k)
     assert not df.status().any()
     df.close()
+
+
+def test_device_frames_screen_on_off(reference):
+    """80 robots (one CTA per robot: the form the fp32 screen runs in) tracked for a few scans with the screen on and off:
+    bit-identical poses, and the screen did settle evaluations."""
+    from ndtpso_slam_b200 import dframes
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    n, steps = 80, 4
+    room = syn.Room(S)
+    scans = [np.stack([syn.make_scan(room, s, (0.03 * k + 0.002 * r, 0.01 * k, 0.004 * k - 0.0005 * r), syn.NoiseLCG(900 + 7 * k + r)) for r in range(n)])
+             for k in range(steps)]
+    conf = capi.PsoConfig.make(population=30, iterations=20)
+    out = {}
+    for scr in (0, 1):
+        cx = capi.Context(0)
+        cx.set_option(capi.OPT_SCREEN, scr)
+        df = dframes.DeviceFrames(cx, n, S, S, cfg.cell_side, s.beams)
+        poses = []
+        for k in range(steps):
+            p, _ = df.track_step(scans[k], s.angle_min, s.angle_increment, s.range_max, conf=conf)
+            poses.append(p)
+        out[scr] = (np.array(poses), df.pso_stats())
+        assert not df.status().any()
+        df.close()
+        cx.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert (out[0][1][:, 3] == 0).all() and out[1][1][:, 3].sum() > 0
+    assert np.abs(out[1][0][-1][:, 0] - 0.09).max() < 0.05  # and the robots were tracked (x advances 3 cm per scan)

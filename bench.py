@@ -219,7 +219,7 @@ def run_tracking(B, conf, steps, device, groups=2):
     cfg = syn.CFG2
     s, S = cfg.sensor, cfg.map_size_m
     room = syn.Room(S)
-    groups = max(1, min(groups, B // 96)) if B >= 96 else 1  # a group smaller than ~75 problems would be spread over clusters
+    groups = max(1, min(groups, B // 32))
     bounds = [(g * B // groups, (g + 1) * B // groups) for g in range(groups)]
     sets = [syn.trajectory_problem(cfg, b) for b in range(B)]
     scans = [np.stack([syn.make_scan(room, s, (ss.true_pose[0] + 0.02 * k, ss.true_pose[1] + 0.005 * k, ss.true_pose[2] + 0.001 * k),
@@ -228,7 +228,7 @@ def run_tracking(B, conf, steps, device, groups=2):
     ctxs, dfs = [], []
     for lo, hi in bounds:
         c = capi.Context(device)
-        df = dframes.DeviceFrames(c, hi - lo, S, S, cfg.cell_side, s.beams, max_cells=1024)
+        df = dframes.DeviceFrames(c, hi - lo, S, S, cfg.cell_side, s.beams, max_cells=1024, flags=dframes.DF_NO_CLUSTER if groups > 1 else 0)
         for k in range(5):  # the map: 5 scans per robot merged at their known poses
             df.load_laser(np.stack([ss.map_scans[k][1] for ss in sets[lo:hi]]), s.angle_min, s.angle_increment, s.range_max)
             df.update(np.array([ss.map_scans[k][0] for ss in sets[lo:hi]]))

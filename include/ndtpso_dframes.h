@@ -60,8 +60,14 @@ typedef struct ndtpso_dframes_config {
   int32_t window_points;/* points kept per cell for the sliding window (ring, power of two); the
                            statistics are exact while the last NDT_WINDOW_SIZE slots fit; 0 = auto */
   float laser_ignore_epsilon; /* NDTPSOConfig::laserIgnoreEpsilon (config.h:6,44), default 0.1f */
-  int32_t reserved;     /* must be 0 */
+  int32_t flags;        /* NDTPSO_DF_* creation flags, 0 by default */
 } ndtpso_dframes_config;
+
+/* creation flags */
+enum {
+  NDTPSO_DF_NO_CLUSTER = 1 /* never spread one frame's match over a thread-block cluster (the low-latency form for few frames):
+                              for callers that keep several groups of frames in flight on their own streams */
+};
 
 /* per-frame status bits (ndtpso_dframes_status) */
 enum {

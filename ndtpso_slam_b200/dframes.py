@@ -20,6 +20,7 @@ from . import capi
 
 RNG_SEEDED, RNG_CONTINUE = 0, 1
 DF_CELL_POOL_FULL, DF_WINDOW_TRUNCATED, DF_INDEX_PAST_END, DF_IRREGULAR_SIGMA = 1, 2, 4, 8
+DF_NO_CLUSTER = 1  # creation flag
 
 #: every symbol include/ndtpso_dframes.h declares
 EXPORTS = [
@@ -34,7 +35,7 @@ class DFramesConfig(C.Structure):
     """struct ndtpso_dframes_config."""
     _fields_ = [("n_frames", C.c_int32), ("width_m", C.c_int32), ("height_m", C.c_int32), ("max_beams", C.c_int32),
                 ("cell_side", C.c_double), ("scan_cell_side", C.c_double), ("max_cells", C.c_int32), ("window_points", C.c_int32),
-                ("laser_ignore_epsilon", C.c_float), ("reserved", C.c_int32)]
+                ("laser_ignore_epsilon", C.c_float), ("flags", C.c_int32)]
 
 
 _bound = False
@@ -76,7 +77,7 @@ class DeviceFrames:
     """n reference frames resident on the GPU of `ctx` (a capi.Context)."""
 
     def __init__(self, ctx, n_frames, width_m, height_m, cell_side, max_beams, scan_cell_side=0.0, max_cells=0, window_points=0,
-                 laser_ignore_epsilon=0.1):
+                 laser_ignore_epsilon=0.1, flags=0):
         self.L = _lib()
         self.ctx = ctx
         cfg = DFramesConfig()
@@ -85,6 +86,7 @@ class DeviceFrames:
         cfg.cell_side, cfg.scan_cell_side = float(cell_side), float(scan_cell_side)
         cfg.max_cells, cfg.window_points = int(max_cells), int(window_points)
         cfg.laser_ignore_epsilon = float(laser_ignore_epsilon)
+        cfg.flags = int(flags)
         self.cfg = cfg
         self.n = int(n_frames)
         self.h = C.c_void_p()

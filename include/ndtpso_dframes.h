@@ -122,6 +122,12 @@ int ndtpso_dframes_track_step(ndtpso_dframes* df, const float* ranges, int32_t n
                               float range_max, const double* initial_poses, const ndtpso_pso_config* conf, int32_t rng_mode,
                               const uint32_t* seeds, double* out_pose, double* out_cost);
 
+/* Multi-GPU: robots are split over ranks (one process and one ndtpso_dframes per GPU).  With an exchange attached
+ * (ndtpso_exchange_*, ndtpso_b200.h; n_per_rank == n_frames) every later align / track_step also stores its poses into
+ * the gathered buffer of every rank from the PSO kernel's epilogue; ndtpso_exchange_wait / _results then give every
+ * rank all robots' poses.  ex = NULL detaches. */
+int ndtpso_dframes_attach_exchange(ndtpso_dframes* df, ndtpso_exchange* ex);
+
 /* ---- read-back (synchronises) ---------------------------------------------------- */
 /* dense table of one frame: mean [C][2], inv_cov [C][4], built [C], C = w_cells*h_cells */
 int ndtpso_dframes_download_map(ndtpso_dframes* df, int32_t frame, double* mean, double* inv_cov, uint8_t* built);

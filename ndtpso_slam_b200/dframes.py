@@ -28,6 +28,7 @@ EXPORTS = [
     "ndtpso_dframes_load_laser", "ndtpso_dframes_set_scan_points", "ndtpso_dframes_update", "ndtpso_dframes_build",
     "ndtpso_dframes_align", "ndtpso_dframes_track_step", "ndtpso_dframes_download_map", "ndtpso_dframes_download_scan",
     "ndtpso_dframes_info", "ndtpso_dframes_status", "ndtpso_dframes_pso_stats", "ndtpso_dframes_kernel_times",
+    "ndtpso_dframes_attach_exchange",
 ]
 
 
@@ -64,6 +65,7 @@ def _lib():
         L.ndtpso_dframes_info.argtypes = [vp, i32, vp]
         L.ndtpso_dframes_status.argtypes = [vp, vp]
         L.ndtpso_dframes_pso_stats.argtypes = [vp, vp]
+        L.ndtpso_dframes_attach_exchange.argtypes = [vp, vp]
         L.ndtpso_dframes_kernel_times.argtypes = [vp, vp]
         _bound = True
     return L
@@ -180,6 +182,10 @@ class DeviceFrames:
         out = np.zeros(self.n, dtype=np.int32)
         self._check(self.L.ndtpso_dframes_status(self.h, _p(out)))
         return out
+
+    def attach_exchange(self, ex):
+        """Every later align / track_step also publishes its poses through `ex` (a capi.Exchange with n_per_rank == n_frames)."""
+        self._check(self.L.ndtpso_dframes_attach_exchange(self.h, ex.h if ex is not None else None))
 
     def pso_stats(self) -> np.ndarray:
         """[n, 4] of the last align: rounds, gbest updates, fp64 cost evaluations, evaluations settled by the fp32 screen."""

@@ -74,3 +74,37 @@ def test_exchange_wait_times_out_instead_of_hanging(ctx, golden):
     bt.close()
     a.close()
     b.close()
+
+
+def test_device_frames_publish_through_the_exchange():
+    """Two ranks (contexts of one process), each tracking its own robots with device-resident maps: after a step every rank
+    holds all robots' poses, delivered by the PSO kernel's epilogue."""
+    from ndtpso_slam_b200 import dframes, synthetic as syn
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    world, n = 2, 3
+    ndev = capi.load_library().ndtpso_device_count()
+    room = syn.Room(S)
+    ctxs = [capi.Context(r % ndev) for r in range(world)]
+    dfs = [dframes.DeviceFrames(ctxs[r], n, S, S, cfg.cell_side, s.beams) for r in range(world)]
+    exs = [capi.Exchange(ctxs[r], world, r, n) for r in range(world)]
+    for r in range(world):
+        exs[r].connect_local(exs)
+        dfs[r].attach_exchange(exs[r])
+    conf = capi.PsoConfig.make(population=20, iterations=10)
+    for k in range(3):
+        mine = []
+        for r in range(world):
+            scans = np.stack([syn.make_scan(room, s, (0.03 * k + 0.01 * (r * n + i), 0.01 * k, 0.004 * k), syn.NoiseLCG(40 + 10 * k + r * n + i))
+                              for i in range(n)])
+            mine.append(dfs[r].track_step(scans, s.angle_min, s.angle_increment, s.range_max, conf=conf)[0])
+        if k == 0:
+            continue  # the first scan is not matched: nothing is published
+        want = np.concatenate(mine)
+        for r in range(world):
+            pose, _ = exs[r].results()
+            assert np.array_equal(pose, want), (k, r)
+    for r in range(world):
+        dfs[r].close()
+        exs[r].close()
+        ctxs[r].close()

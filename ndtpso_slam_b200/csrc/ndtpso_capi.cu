@@ -13,7 +13,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -208,22 +212,96 @@ int validate_problem(ndtpso_ctx* ctx, const ndtpso_problem& p, int b) {
   return NDTPSO_OK;
 }
 
+// Persistent host workers for the staging loops (table scans, gathers, memcpy): spawning threads per batch cost more than
+// the loops themselves once several ranks share a host.  One pool per process; run() hands out indices in small chunks,
+// the calling thread works too, and calls are serialised (contexts of one process stage one batch at a time).
+class HostPool {
+ public:
+  static HostPool& instance() {
+    static HostPool pool;
+    return pool;
+  }
+  template <class F>
+  void run(int n, int max_threads, F f) {
+    const int want = std::min<int>(std::min<int>(max_threads, (int)workers_.size() + 1), n / 8);  // not worth a thread for fewer than 8 items
+    if (want <= 1) {
+      for (int i = 0; i < n; ++i) f(i);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(run_mutex_);
+    std::function<void(int)> fn = f;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &fn;
+      n_ = n;
+      next_.store(0);
+      active_ = want - 1;   // workers that should join in
+      running_ = want - 1;  // workers that have not finished yet
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work(fn, n);
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return running_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int nw = std::max(0, std::min(7, hw - 1));
+    for (int t = 0; t < nw; ++t) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  void work(std::function<void(int)>& fn, int n) {
+    for (;;) {
+      const int i0 = next_.fetch_add(4);
+      if (i0 >= n) break;
+      for (int i = i0; i < std::min(n, i0 + 4); ++i) fn(i);
+    }
+  }
+  void loop() {
+    unsigned seen = 0;
+    for (;;) {
+      std::function<void(int)>* fn = nullptr;
+      int n = 0;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && active_ > 0); });
+        if (stop_) return;
+        seen = epoch_;
+        --active_;
+        fn = job_;
+        n = n_;
+      }
+      work(*fn, n);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--running_ == 0) done_cv_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, run_mutex_;
+  std::condition_variable cv_, done_cv_;
+  std::function<void(int)>* job_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, active_ = 0, running_ = 0;
+  unsigned epoch_ = 0;
+  bool stop_ = false;
+};
+
 // Runs f(i) for i in [0, n) on up to `max_threads` host threads (staging is memcpy/scan bound).
 template <class F>
 void parallel_for(int n, int max_threads, F f) {
-  int nt = std::min<int>(max_threads, (int)std::thread::hardware_concurrency());
-  nt = std::min(nt, n / 8);  // not worth a thread for fewer than 8 items
-  if (nt <= 1) {
-    for (int i = 0; i < n; ++i) f(i);
-    return;
-  }
-  std::vector<std::thread> th;
-  th.reserve(nt);
-  for (int t = 0; t < nt; ++t)
-    th.emplace_back([=]() {
-      for (int i = t; i < n; i += nt) f(i);
-    });
-  for (auto& x : th) x.join();
+  HostPool::instance().run(n, max_threads, f);
 }
 
 // What the host learns from one pass over a table: which cells are built, the grid rows they
@@ -494,10 +572,13 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     if (p.n_points) memcpy(h + o_pts[b], p.points_xy, (size_t)p.n_points * 16);
     if (conf && p.rand_stream) memcpy(h + o_rnd[b], p.rand_stream, (size_t)prm.n_draws * 4);
     double pm = 0.;
-    for (int i = 0; i < 2 * p.n_points; ++i) pm = std::max(pm, std::fabs(p.points_xy[i]));
-    pmax_of[b] = pm;  // NaN compares false and is caught below
-    for (int i = 0; i < 2 * p.n_points; ++i)
-      if (!(std::fabs(p.points_xy[i]) <= 1e30)) pmax_of[b] = INFINITY;
+    bool finite = true;
+    for (int i = 0; i < 2 * p.n_points; ++i) {
+      const double v = std::fabs(p.points_xy[i]);
+      pm = v > pm ? v : pm;
+      finite = finite && (v <= 1e30);  // false for NaN too
+    }
+    pmax_of[b] = finite ? pm : INFINITY;
   });
   for (int b = 0; b < n; ++b) bt->scr_pmax = std::max(bt->scr_pmax, pmax_of[b]);
   int need = 0;

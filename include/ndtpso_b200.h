@@ -148,6 +148,13 @@ int ndtpso_align_collect(ndtpso_batch* batch, double* out_pose /* [n][3] */, dou
 int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int32_t n_poses,
                       const double* poses /* [n][n_poses][3] */, double* out_cost /* [n][n_poses] */);
 
+/* The rigorous fp32 lower bound the point-sliced PSO kernel screens its candidates with (NDTPSO_OPT_SCREEN), for
+ * `n_poses` (<= 1024) candidate poses per problem: out_lower[b][k] <= cost_function(poses[b][k]) always.  The PSO never
+ * returns these; the entry point exists so that the bound can be checked pose by pose.  NDTPSO_ERR_LIMIT when the batch
+ * does not qualify for the screen (frames that are not square, whole, power-of-two cells; irregular Sigma^-1). */
+int ndtpso_screen_bounds(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int32_t n_poses,
+                         const double* poses /* [n][n_poses][3] */, double* out_lower /* [n][n_poses] */);
+
 /* ---- the same path with the batch kept resident in HBM -------------------------- */
 /* upload (H2D, asynchronous on the context's stream) */
 int ndtpso_batch_create(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf,

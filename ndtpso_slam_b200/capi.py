@@ -24,7 +24,7 @@ KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 EXPORTS = [
     "ndtpso_abi_version", "ndtpso_pso_config_default", "ndtpso_device_count", "ndtpso_ctx_create", "ndtpso_ctx_destroy",
     "ndtpso_ctx_set_stream", "ndtpso_last_error", "ndtpso_ctx_set_option", "ndtpso_rand_draws", "ndtpso_align_batch", "ndtpso_align_submit", "ndtpso_align_collect",
-    "ndtpso_cost_batch", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
+    "ndtpso_cost_batch", "ndtpso_screen_bounds", "ndtpso_batch_create", "ndtpso_batch_solve", "ndtpso_batch_device_results", "ndtpso_batch_results",
     "ndtpso_batch_stats", "ndtpso_batch_stats_ex", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
     "ndtpso_exchange_create", "ndtpso_exchange_connect", "ndtpso_exchange_connect_local", "ndtpso_batch_attach_exchange", "ndtpso_exchange_wait",
     "ndtpso_exchange_device_results", "ndtpso_exchange_results", "ndtpso_exchange_destroy",
@@ -90,6 +90,7 @@ def load_library(build_if_missing: bool = True):
     L.ndtpso_align_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
     L.ndtpso_align_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndtpso_cost_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.c_int32, C.c_void_p, C.c_void_p]
+    L.ndtpso_screen_bounds.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.c_int32, C.c_void_p, C.c_void_p]
     L.ndtpso_batch_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
     L.ndtpso_batch_solve.argtypes = [C.c_void_p]
     L.ndtpso_batch_device_results.argtypes = [C.c_void_p]
@@ -319,6 +320,18 @@ class Context:
         poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(ps.n, -1, 3)
         out = np.empty(poses.shape[:2], dtype=np.float64)
         self._check(self.lib.ndtpso_cost_batch(self.h, ps.n, ps.array, poses.shape[1], _ptr(poses), _ptr(out)))
+        return out
+
+    def screen_bounds(self, flats, poses):
+        """The fp32 screen's lower bound of cost_function for poses[n, m, 3]: returns lower[n, m] (<= cost always)."""
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(ps.n, -1, 3)
+        out = np.empty((ps.n, poses.shape[1]), dtype=np.float64)
+        for k0 in range(0, poses.shape[1], 48):  # the kernel's shared-memory arrays grow with the number of poses per launch
+            chunk = np.ascontiguousarray(poses[:, k0:k0 + 48])
+            part = np.empty((ps.n, chunk.shape[1]), dtype=np.float64)
+            self._check(self.lib.ndtpso_screen_bounds(self.h, ps.n, ps.array, chunk.shape[1], _ptr(chunk), _ptr(part)))
+            out[:, k0:k0 + 48] = part
         return out
 
     def batch(self, flats, conf: PsoConfig) -> Batch:

@@ -868,6 +868,17 @@ int launch_rng(ndtpso_batch* bt) {
   return NDTPSO_OK;
 }
 
+template <int NPT>
+int launch_screen_bound(ndtpso_batch* bt, int nw, int smem, const PsoParams& prm, int m, const double* d_poses, double* d_out) {
+  ndtpso_ctx* ctx = bt->ctx;
+  auto kern = screen_bound_kernel<NPT, 640>;
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+  kern<<<bt->n, nw * 32, smem, ctx->stream>>>(bt->d_probs, bt->d_maps, prm, m, d_poses, d_out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return NDTPSO_OK;
+}
+
 int launch_compact(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   if (bt->n_maps == 0) return NDTPSO_OK;
@@ -1282,6 +1293,57 @@ int ndtpso_cost_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems
   if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
   ctx->launches++;
   e = cudaMemcpyAsync(out_cost, d + o_dev, cost_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
+  return cleanup(NDTPSO_OK);
+}
+
+int ndtpso_screen_bounds(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, int32_t n_poses, const double* poses, double* out_lower) {
+  if (!ctx || n_poses < 0 || n_poses > 1024 || (n > 0 && n_poses > 0 && (!poses || !out_lower)))
+    return fail(ctx, NDTPSO_ERR_ARG, "screen_bounds: null argument or more than 1024 poses");
+  if (n == 0 || n_poses == 0) return NDTPSO_OK;
+  const size_t pose_bytes = sizeof(double) * 3 * (size_t)n * n_poses;
+  const size_t out_bytes = sizeof(double) * (size_t)n * n_poses;
+  ndtpso_batch* bt = nullptr;
+  size_t o_up = 0, o_dev = 0;
+  int rc = batch_build(ctx, n, problems, nullptr, true, pose_bytes, out_bytes, &bt, &o_up, &o_dev);
+  if (rc) return rc;
+  auto cleanup = [&](int code) {
+    ndtpso_batch_destroy(bt);
+    return code;
+  };
+  PsoParams prm{};
+  prm.P = n_poses - 1;
+  const int saved = ctx->opt_screen;
+  ctx->opt_screen = 1;
+  const bool ok = bt->all_compact && bt->all_symmetric && screen_params(bt, &prm);
+  ctx->opt_screen = saved;
+  if (!ok) return cleanup(fail(ctx, NDTPSO_ERR_LIMIT, "screen_bounds: the batch does not qualify for the fp32 screen"));
+  const int npts = std::max(bt->max_pts, 1);
+  int npt = 1;
+  while (npt <= kSlicedMaxNPT && (npts + 32 * npt - 1) / (32 * npt) > 20) ++npt;
+  if (npt > kSlicedMaxNPT) return cleanup(fail(ctx, NDTPSO_ERR_LIMIT, "screen_bounds: scan too long"));
+  const int nw = std::max((npts + 32 * npt - 1) / (32 * npt), 4);
+  const int smem = round16(sliced_smem_bytes(prm.P, nw, 0, bt->max_table_smem, bt->max_n_rec + 1));
+  if (smem > ctx->max_smem_optin) return cleanup(fail(ctx, NDTPSO_ERR_LIMIT, "screen_bounds: tables too large for shared memory"));
+  memcpy(static_cast<unsigned char*>(bt->pin.ptr) + o_up, poses, pose_bytes);
+  rc = batch_upload(bt);
+  if (rc) return cleanup(rc);
+  rc = launch_compact(bt);
+  if (rc) return cleanup(rc);
+  unsigned char* d = static_cast<unsigned char*>(bt->dev.ptr);
+  const double* d_poses = reinterpret_cast<const double*>(d + o_up);
+  double* d_out = reinterpret_cast<double*>(d + o_dev);
+  switch (npt) {
+    case 1: rc = launch_screen_bound<1>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+    case 2: rc = launch_screen_bound<2>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+    case 3: rc = launch_screen_bound<3>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+    case 4: rc = launch_screen_bound<4>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+    case 5: rc = launch_screen_bound<5>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+    default: rc = launch_screen_bound<6>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+  }
+  if (rc) return cleanup(rc);
+  cudaError_t e = cudaMemcpyAsync(out_lower, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cleanup(fail(ctx, NDTPSO_ERR_CUDA, cudaGetErrorString(e)));
   return cleanup(NDTPSO_OK);

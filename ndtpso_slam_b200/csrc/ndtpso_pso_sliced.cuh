@@ -1006,6 +1006,50 @@ __global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem
   if (threadIdx.x == 0 && tp.rank == 0) publish_result(prm.ex, b, gridDim.x / CL, o);  // the thread that wrote o
 }
 
+// The screen's lower bound for given poses (ndtpso_screen_bounds): the very code phase B1 runs, so that tests can check
+// "bound <= fp64 cost" pose by pose instead of only through the decisions it leads to.  One CTA per problem, T threads holding
+// NPT points each; poses [n][m][3], out [n][m].  prm.P = m - 1 sizes the shared-memory arrays.
+template <int NPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) screen_bound_kernel(const DevProblem* __restrict__ probs, const DevMap* __restrict__ maps, PsoParams prm,
+                                                              int m_poses, const double* __restrict__ poses, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const DevProblem& pr = probs[b];
+  const DevMap& mp = maps[pr.map_id];
+  const Topo tp = make_topo<1>(1);
+  SliceCtx m;
+  ScreenCtx sc;
+  double2 pt[NPT];
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt, 1, &sc, &prm);
+  const int tid = threadIdx.x, T = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < m_poses; j += T) {
+    const double* p = poses + 3 * ((size_t)b * m_poses + j);
+    double s, c;
+    sincos(p[2], &s, &c);
+    sm.pose32[j] = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(c), static_cast<float>(s));
+  }
+  __syncthreads();
+  float2 px2[NPT], py2[NPT];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const float fx = static_cast<float>(fmin(pt[k].x, 1e30)), fy = static_cast<float>(pt[k].y);
+    px2[k] = make_float2(fx, fx);
+    py2[k] = make_float2(fy, fy);
+  }
+  {
+    int j = 0;
+    for (; j + 8 <= m_poses; j += 8) screen_batch<NPT, 8>(sc, px2, py2, sm.pose32, sm.lbpart, j, m_poses, tp.NW, warp, lane);
+    for (; j + 4 <= m_poses; j += 4) screen_batch<NPT, 4>(sc, px2, py2, sm.pose32, sm.lbpart, j, m_poses, tp.NW, warp, lane);
+    for (; j < m_poses; j += 2) screen_batch<NPT, 2>(sc, px2, py2, sm.pose32, sm.lbpart, j, m_poses, tp.NW, warp, lane);
+  }
+  __syncthreads();
+  for (int j = tid; j < m_poses; j += T) {
+    double u = 0.;
+    for (int w2 = 0; w2 < tp.NW; ++w2) u += static_cast<double>(sm.lbpart[j * tp.NW + w2]);
+    out[(size_t)b * m_poses + j] = mp.fast_geom ? -(u * (1. + 6.103515625e-5)) - 1e-6 : -1e300;  // the same slack as phase B1
+  }
+}
+
 // Phase-B microbenchmark: every CTA stages problem blockIdx.x % n_problems and scores `ncand`
 // synthetic candidates around its guess `reps` times.  out[blockIdx.x] = a checksum.
 template <int NPT, int JB, int VAR, int MAXT, int MINB>

@@ -350,3 +350,55 @@ def test_fp32_screen_on_random_tables(oracle):
         po, co, _ = oracle.pso(flats[i], flats[i]["guess"], flats[i]["deviation"], 40, 15, seed=flats[i]["seed"])
         assert np.abs(out[1][0][i] - po).max() <= POSE_ATOL
         assert rel_err(out[1][1][i], co) <= SCORE_RTOL
+
+
+def _check_bounds(ctx, flat, poses, what):
+    lower = ctx.screen_bounds([flat], poses[None])[0]
+    cost = ctx.cost_batch([flat], poses[None])[0]
+    bad = lower > cost  # a lower bound above the fp64 cost would be a bug in the screen, whether or not it flips a decision
+    assert not bad.any(), (what, poses[bad][:3], lower[bad][:3], cost[bad][:3])
+    return lower, cost
+
+
+def test_fp32_screen_bound_pose_by_pose(golden, ctx):
+    """ndtpso_screen_bounds runs the screen's own code: for thousands of poses — near the optimum, spread like a swarm, far
+    outside the map, on cell edges — the bound never exceeds the fp64 cost, and it is tight where it matters."""
+    rng = np.random.default_rng(3)
+    for name in ("cfg2", "traj17", "cfg1", "cfg5_0.25", "cfg5_2.0"):
+        flat = golden.flat(name)
+        c = golden.case(name)
+        best = c["pose"][0]
+        sets = [best + rng.normal(size=(256, 3)) * np.array([0.002, 0.002, 0.0005]),     # a converged swarm
+                best + rng.normal(size=(256, 3)) * np.array([0.1, 0.1, 0.01]),           # the initial spread
+                best + rng.normal(size=(256, 3)) * np.array([2.0, 2.0, 0.5]),            # diverged particles
+                best + rng.uniform(-1, 1, size=(128, 3)) * np.array([60.0, 60.0, 6.0]),  # far outside the map
+                np.concatenate([np.round(best[:2] * 4) / 4 + rng.integers(-3, 4, size=(128, 2)) * 0.25, np.zeros((128, 1))], 1)]
+        tight = []
+        for k, poses in enumerate(sets):
+            lower, cost = _check_bounds(ctx, flat, poses, (name, k))
+            if k == 0:
+                tight.append(np.median((cost - lower) / np.abs(cost)))
+        assert tight[0] < (0.10 if name == "cfg5_0.25" else 0.05), (name, tight)  # close to the true cost near the optimum (0.25 m cells: 6.5 %)
+
+
+def test_fp32_screen_bound_on_random_tables(ctx):
+    """The same on random sharp / strongly correlated tables, with scan points on cell edges and on the frame's border."""
+    rng = np.random.default_rng(8)
+    gw = gh = 40
+    n = gw * gh
+    for trial in range(4):
+        built = (rng.random(n) < 0.3).astype(np.uint8)
+        ix, iy = np.arange(n) % gw, np.arange(n) // gw
+        mean = np.stack([(ix + rng.random(n)) * 0.5 - 10.0, (iy + rng.random(n)) * 0.5 - 10.0], 1)
+        scale = 10.0 ** rng.uniform(0.0, 6.5, n)
+        a, b = scale * rng.uniform(0.2, 1.0, n), scale * rng.uniform(0.2, 1.0, n)
+        r = rng.choice([0.0, 0.5, 0.99, 0.9999], n) * rng.choice([-1.0, 1.0], n) * np.sqrt(a * b)
+        icov = np.stack([a, r, r, b], 1)
+        pts = rng.uniform(-9.5, 9.5, size=(1000, 2))
+        pts[:100] = np.round(pts[:100] * 2) / 2
+        pts[100:130, 0] = 10.0 - 1e-9 * rng.random(30)
+        flat = dict(points=pts, mean=mean, inv_cov=icov, built=built, w_cells=gw, h_cells=gh, width_m=20.0, height_m=20.0,
+                    cell_side=0.5, x_min=-10.0, x_max=10.0, y_min=-10.0, y_max=10.0)
+        poses = np.concatenate([rng.normal(size=(400, 3)) * np.array([0.3, 0.3, 0.05]), np.zeros((8, 3)),
+                                rng.uniform(-1, 1, size=(104, 3)) * np.array([25.0, 25.0, 3.2])])
+        _check_bounds(ctx, flat, poses, trial)

@@ -50,50 +50,99 @@ def make_problems(batch, rank):
     return workload.cfg2_batch(batch, first=rank * batch)
 
 
+def workload_name(batch):
+    """config.workload of both arms (the reference arm runs a bounded sample of the same workload)."""
+    return (f"cfg2 shape (configs[1]; batched as configs[2]): {batch} independent 1081-beam scan-matches per GPU vs "
+            "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations")
+
+
 # ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled while the timed regions run.  In-process NVML (5 ms period; works
+    for short regions and for eight ranks at once); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.source = index, [], None, None, None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES reorders devices: go by UUID
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.sm_max = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown, n.nvmlClocksEventReasonSwThermalSlowdown,
+                n.nvmlClocksEventReasonSwPowerCap]
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([sm, self.sm_max, 0.0] + ["active" if mask & b else "not active" for b in bits])
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        else:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
+            for n, v in zip(self.NAMES, r[3:7]):
+                if str(v).lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "source": self.source, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -173,8 +222,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": args.gpus, "steps": len(rates),
             "warmup": args.warmup, "ms_per_step": 1e3 * base["cores"] * per_step / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 (configs[1] shape): 1081-beam scan vs 50 m/0.5 m NDT map, 70 particles x 50 iterations; "
-                                   "bounded sample on the host cores", "particles": P, "iterations": I},
+            "config": {"workload": workload_name(args.batch), "batch_per_gpu": args.batch, "particles": P, "iterations": I,
+                       "sample": f"each step: {base['cores']} x {per_step} matches of that workload (its first trajectory problems, own map "
+                                 "each) on the host cores, one single-thread worker per core"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "scan-matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -510,8 +560,7 @@ def _run_gpu_arm(args, real_stdout):
             "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"cfg2 shape (configs[1]; batched as configs[2]): {B} independent 1081-beam scan-matches per GPU vs "
-                                   "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations",
+            "config": {"workload": workload_name(B),
                        "batch_per_gpu": B, "particles": P, "iterations": I,
                        "l2": "inputs larger than L2: four resident copies of the batch (4 x 130 MB of dense tables, of which a step touches ~41 MB: "
                              "built flags, built cells, compact tables, rand streams) are used round-robin, 164 MB between two uses of a copy",

@@ -51,12 +51,23 @@ typedef struct ndtpso_pso_config {
   int32_t iterations;   /* PSOConfig::iterations      default 50  (PSO_ITERATIONS) */
   int32_t population;   /* PSOConfig::populationSize  default 30  (PSO_POPULATION_SIZE) */
   int32_t num_threads;  /* PSOConfig::num_threads     default -1 */
-  int32_t reserved;     /* must be 0 */
+  int32_t variant;      /* NDTPSO_VARIANT_*: which of the reference's two optimisers runs (0 = pso_optimization);
+                           occupies the padding of the reference's PSOConfig, so the layout is unchanged */
   double w;             /* coeff.w          default .8 */
   double c1;            /* coeff.c1         default 2. */
   double c2;            /* coeff.c2         default 2. */
   double w_dumping;     /* coeff.w_dumping  default 1. */
 } ndtpso_pso_config;
+
+/* ndtpso_pso_config::variant */
+enum {
+  NDTPSO_VARIANT_PSO = 0,  /* pso_optimization       lib/ndtpso_slam/core.cpp:50-116: what NDTFrame::align() runs */
+  NDTPSO_VARIANT_GLIR = 1  /* glir_pso_optimization  lib/ndtpso_slam/core.cpp:118-186 (decl core.h:21-22): the GLIR-PSO variant the
+                              reference ships as "UNTESTED" and never calls.  omega, c1 = c2 and a best-position ratio are
+                              recomputed per particle from the best costs; w, c1, c2, w_dumping are ignored; the reference
+                              fixes its population to PSO_POPULATION_SIZE (30), here `population` is honoured.  Runs on the
+                              generic warp-per-particle kernel.  It draws 3(P + 2) + 6PI random numbers. */
+};
 
 /* Fills *conf with the reference defaults (what 2-argument NDTFrame::align() runs). */
 void ndtpso_pso_config_default(ndtpso_pso_config* conf);

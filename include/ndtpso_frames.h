@@ -37,6 +37,9 @@ int ndtpso_frame_align(ndtpso_frame* ref_frame, const double* guess /* [3] */, n
 /* the same with an explicit PSOConfig (conf != NULL) */
 int ndtpso_frame_align_conf(ndtpso_frame* ref_frame, const double* guess, ndtpso_frame* new_frame, const ndtpso_pso_config* conf,
                             double* out_pose);
+/* glir_pso_optimization (core.h:21-23, core.cpp:118-186): population PSO_POPULATION_SIZE, process-global rand() stream */
+int ndtpso_frame_glir(ndtpso_frame* ref_frame, const double* guess /* [3] */, ndtpso_frame* new_frame, unsigned int iterations,
+                      const double* deviation /* [3] */, double* out_pose /* [3] */);
 /* cost_function (core.h:49) */
 int ndtpso_frame_cost(ndtpso_frame* ref_frame, ndtpso_frame* new_frame, const double* pose /* [3] */, double* out_cost);
 /* NDTFrame::addPose / NDTFrame::dumpMap (ndtframe.cpp:200-206,268-391): <filename>.pose.csv, .map.csv, .gnuplot */

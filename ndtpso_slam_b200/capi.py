@@ -32,14 +32,18 @@ EXPORTS = [
 IPC_HANDLE_BYTES, MAX_RANKS = 64, 8
 
 
+VARIANT_PSO, VARIANT_GLIR = 0, 1  # ndtpso_pso_config::variant
+
+
 class PsoConfig(C.Structure):
     """struct ndtpso_pso_config == reference PSOConfig (include/ndtpso_slam/config.h:27-38)."""
-    _fields_ = [("iterations", C.c_int32), ("population", C.c_int32), ("num_threads", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("iterations", C.c_int32), ("population", C.c_int32), ("num_threads", C.c_int32), ("variant", C.c_int32),
                 ("w", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("w_dumping", C.c_double)]
 
     @classmethod
-    def make(cls, population=30, iterations=50, w=0.8, c1=2.0, c2=2.0, w_dumping=1.0):
-        return cls(int(iterations), int(population), -1, 0, w, c1, c2, w_dumping)
+    def make(cls, population=30, iterations=50, w=0.8, c1=2.0, c2=2.0, w_dumping=1.0, variant=0):
+        """variant: VARIANT_PSO (pso_optimization, core.cpp:50-116) or VARIANT_GLIR (glir_pso_optimization, core.cpp:118-186)."""
+        return cls(int(iterations), int(population), -1, int(variant), w, c1, c2, w_dumping)
 
 
 class MapView(C.Structure):

@@ -374,6 +374,9 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   PsoParams prm{};
   if (conf) {
     if (conf->iterations < 0 || conf->population < 0) return fail(ctx, NDTPSO_ERR_ARG, "PSO config: negative iterations/population");
+    if (conf->variant != NDTPSO_VARIANT_PSO && conf->variant != NDTPSO_VARIANT_GLIR)
+      return fail(ctx, NDTPSO_ERR_ARG, "PSO config: unknown variant");
+    prm.variant = conf->variant;
     const int64_t draws = ndtpso_rand_draws(conf);
     if (draws > INT_MAX / 2) return fail(ctx, NDTPSO_ERR_LIMIT, "PSO config: 3+3P+6PI exceeds the supported stream length");
     prm.P = conf->population;
@@ -840,9 +843,10 @@ void exchange_arm(ndtpso_batch* bt) {
 // (any scan length, any table size)
 int launch_pso_any(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
-  int rc = ctx->opt_kernel == 1 ? 1 : launch_sliced(bt);
+  const bool glir = bt->prm.variant == NDTPSO_VARIANT_GLIR;  // the point-sliced kernel implements pso_optimization only
+  int rc = (ctx->opt_kernel == 1 || glir) ? 1 : launch_sliced(bt);
   if (rc == 1) {
-    if (ctx->opt_kernel == 2) return fail(ctx, NDTPSO_ERR_LIMIT, "batch does not qualify for the point-sliced kernel");
+    if (ctx->opt_kernel == 2 && !glir) return fail(ctx, NDTPSO_ERR_LIMIT, "batch does not qualify for the point-sliced kernel");
     const int fixed = pso_fixed_smem_bytes(bt->prm.P);
     const int smem = pick_smem(ctx, fixed, bt->need_dyn_smem);
     switch (pick_warps(ctx)) {
@@ -899,7 +903,7 @@ void ndtpso_pso_config_default(ndtpso_pso_config* conf) {
   conf->iterations = 50;   // PSO_ITERATIONS        config.h:20
   conf->population = 30;   // PSO_POPULATION_SIZE   config.h:21
   conf->num_threads = -1;  //                       config.h:30
-  conf->reserved = 0;
+  conf->variant = NDTPSO_VARIANT_PSO;
   conf->w = .8;            // PSO_W                 config.h:23
   conf->c1 = 2.;           // PSO_C1                config.h:24
   conf->c2 = 2.;           // PSO_C2                config.h:25
@@ -909,6 +913,7 @@ void ndtpso_pso_config_default(ndtpso_pso_config* conf) {
 int64_t ndtpso_rand_draws(const ndtpso_pso_config* conf) {
   if (!conf) return 0;
   const int64_t P = conf->population, I = conf->iterations;
+  if (conf->variant == NDTPSO_VARIANT_GLIR) return 3 * (P + 2) + 6 * P * I;  // core.cpp:125,132,135,149
   return 3 + 3 * P + 6 * P * I;
 }
 

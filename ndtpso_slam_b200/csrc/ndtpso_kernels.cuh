@@ -77,7 +77,8 @@ struct PeerExchange {
 struct PsoParams {
   int P, I;
   double w, c1, c2, wd;
-  int n_draws;      // 3 + 3P + 6PI
+  int n_draws;      // 3 + 3P + 6PI (GLIR: 3(P + 2) + 6PI)
+  int variant;      // 0 = pso_optimization (core.cpp:50-116), 1 = glir_pso_optimization (core.cpp:118-186; generic kernel only)
   int smem_bytes;   // dynamic shared memory given to pso_kernel
   int hot_chunk;    // point-sliced kernel: speculation window while gbest improves often (0 = always the whole swarm)
   int hot_thresh;   // improvements in an iteration that keep the next one's window small
@@ -512,6 +513,7 @@ struct PsoSmem {
   double* vnew;   // [P][3]
   double* pb;     // [P][3]
   double* pbc;    // [P]
+  double* pavg;   // [P]  Particle::pbest_average (GLIR only)
   unsigned char* dyn;  // start of the staged problem data
   int fixed_bytes;
 };
@@ -520,7 +522,7 @@ __host__ __device__ inline int pso_fixed_smem_bytes(int P) {
   int b = 16;                                       // mbarrier
   b += kExpTableSize * (int)sizeof(double);         // exp table
   b += 2 * (P + 1) * (int)sizeof(Cand);             // candidates, double buffered
-  b += (P > 0 ? P : 1) * 13 * (int)sizeof(double);  // x, v, vnew, pb (3 each) + pbc
+  b += (P > 0 ? P : 1) * 14 * (int)sizeof(double);  // x, v, vnew, pb (3 each) + pbc + pavg
   return (b + 15) & ~15;
 }
 
@@ -536,6 +538,7 @@ __device__ __forceinline__ PsoSmem carve_smem(unsigned char* base, int P) {
   s.vnew = d + 6 * Pn;
   s.pb = d + 9 * Pn;
   s.pbc = d + 12 * Pn;
+  s.pavg = d + 13 * Pn;
   s.fixed_bytes = pso_fixed_smem_bytes(P);
   s.dyn = base + s.fixed_bytes;
   return s;
@@ -691,6 +694,150 @@ __device__ __forceinline__ void pso_body(const Cost& cost, const DevProblem& pr,
 }
 
 // ------------------------------------------------------------------------------------------
+// GLIR variant (glir_pso_optimization, core.cpp:118-186; "UNTESTED" in the reference, which never calls it).  Same
+// warp-per-particle, speculate-and-replay structure as pso_body: a pending particle's candidate depends on the current
+// gbest (position AND cost: omega, c1 = c2 and best_ratio, core.cpp:146-150) and on its own committed state.
+//   * global_best is a particle of its own drawn with the caller's deviation (:125; zero_devi is never used): task 0.
+//   * P + 1 particles are constructed (:132-135), 3(P + 2) draws before the first iteration; particles[P] is never
+//     compared (:137) nor iterated (:145): its draws are skipped over and its cost is not evaluated.
+//   * every operation is a separate IEEE add/multiply/divide in the reference's association order (no contraction).
+// Costs enter the arithmetic here (not only comparisons), so poses follow the reference to rounding-level differences
+// of the cost (~1e-13 relative), not bit for bit.
+// ------------------------------------------------------------------------------------------
+template <class Cost, int NW>
+__device__ __forceinline__ void glir_body(const Cost& cost, const DevProblem& pr, const PsoParams& prm, const PsoSmem& sm,
+                                          double* __restrict__ out, int* __restrict__ stats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = prm.P, I = prm.I;
+  const int* __restrict__ rnd = pr.rnd;
+  Cand* cand0 = sm.cand;
+  Cand* cand1 = sm.cand + (P + 1);
+
+  for (int t = warp; t < P + 1; t += NW) {  // Particle ctor, core.cpp:13-23
+    double pos[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pos[k] = __dadd_rn(pr.guess[k], __dmul_rn(unit_random(rnd[3 * t + k]), pr.dev[k]));
+    const double c = cost(pos[0], pos[1], pos[2], lane);
+    if (lane == 0) cand0[t] = Cand{c, pos[0], pos[1], pos[2]};
+  }
+  __syncthreads();
+  double gbc = cand0[0].c, gb0 = cand0[0].x, gb1 = cand0[0].y, gb2 = cand0[0].th;
+  for (int j = 0; j < P; ++j) {  // core.cpp:137-140, particles[0 .. P-1] in order
+    const Cand cd = cand0[1 + j];
+    if (cd.c < gbc) {
+      gbc = cd.c;
+      gb0 = cd.x;
+      gb1 = cd.y;
+      gb2 = cd.th;
+    }
+  }
+  for (int j = warp + lane * NW; j < P; j += 32 * NW) {
+    const Cand cd = cand0[1 + j];
+    sm.x[3 * j] = cd.x;
+    sm.x[3 * j + 1] = cd.y;
+    sm.x[3 * j + 2] = cd.th;
+    sm.pb[3 * j] = cd.x;
+    sm.pb[3 * j + 1] = cd.y;
+    sm.pb[3 * j + 2] = cd.th;
+    sm.v[3 * j] = sm.v[3 * j + 1] = sm.v[3 * j + 2] = 0.;
+    sm.pbc[j] = cd.c;
+    sm.pavg[j] = cd.c;  // core.cpp:22
+  }
+  __syncwarp();
+
+  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0;
+  while (it < I) {
+    Cand* cand = par ? cand1 : cand0;
+    const int j0 = start + ((warp - start) % NW + NW) % NW;
+    for (int j = j0; j < P; j += NW) {
+      const int base = 3 * (P + 2) + 6 * P * it + 6 * j;
+      double u = 0.;
+      if (lane < 6) u = fabs(unit_random(rnd[base + lane]));  // Array2d::Random().abs(), core.cpp:149
+      const double omega = __dadd_rn(1.1, -__ddiv_rn(gbc, __ddiv_rn(sm.pavg[j], static_cast<double>(j + 1))));  // core.cpp:146
+      const double c12 = __dadd_rn(1.0, __ddiv_rn(gbc, sm.pbc[j]));                                             // core.cpp:147
+      double nx[3], nv[3];
+      const double gb[3] = {gb0, gb1, gb2};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double rx = __shfl_sync(0xffffffffu, u, 2 * k);
+        const double ry = __shfl_sync(0xffffffffu, u, 2 * k + 1);
+        const double xk = sm.x[3 * j + k], vk = sm.v[3 * j + k], pbk = sm.pb[3 * j + k];
+        const double ratio = __ddiv_rn(pbk, gb[k]);  // core.cpp:150
+        // core.cpp:151-153: ((omega*v) + ((c1*rx)*(ratio*pb - x))) + ((c2*ry)*((1./ratio)*gb - x))
+        const double t1 = __dmul_rn(omega, vk);
+        const double t2 = __dmul_rn(__dmul_rn(c12, rx), __dadd_rn(__dmul_rn(ratio, pbk), -xk));
+        const double t3 = __dmul_rn(__dmul_rn(c12, ry), __dadd_rn(__dmul_rn(__ddiv_rn(1., ratio), gb[k]), -xk));
+        nv[k] = __dadd_rn(__dadd_rn(t1, t2), t3);
+        nx[k] = __dadd_rn(xk, nv[k]);  // core.cpp:155
+      }
+      const double c = cost(nx[0], nx[1], nx[2], lane);
+      if (lane == 0) {
+        cand[j] = Cand{c, nx[0], nx[1], nx[2]};
+        sm.vnew[3 * j] = nv[0];
+        sm.vnew[3 * j + 1] = nv[1];
+        sm.vnew[3 * j + 2] = nv[2];
+      }
+    }
+    __syncthreads();
+    int jstar = -1;  // first pending particle that improves gbest (core.cpp:168)
+    for (int base = start; base < P && jstar < 0; base += 32) {
+      const int j = base + lane;
+      const bool imp = (j < P) && (cand[j].c < gbc);
+      const unsigned mask = __ballot_sync(0xffffffffu, imp);
+      if (mask) jstar = base + __ffs(mask) - 1;
+    }
+    const int end = (jstar >= 0) ? jstar + 1 : P;
+    for (int j = j0 + lane * NW; j < end; j += 32 * NW) {  // commit, core.cpp:155-166
+      const Cand cd = cand[j];
+      sm.x[3 * j] = cd.x;
+      sm.x[3 * j + 1] = cd.y;
+      sm.x[3 * j + 2] = cd.th;
+      sm.v[3 * j] = sm.vnew[3 * j];
+      sm.v[3 * j + 1] = sm.vnew[3 * j + 1];
+      sm.v[3 * j + 2] = sm.vnew[3 * j + 2];
+      double pbcj = sm.pbc[j];
+      if (cd.c < pbcj) {
+        pbcj = cd.c;
+        sm.pbc[j] = cd.c;
+        sm.pb[3 * j] = cd.x;
+        sm.pb[3 * j + 1] = cd.y;
+        sm.pb[3 * j + 2] = cd.th;
+      }
+      sm.pavg[j] = __dadd_rn(sm.pavg[j], pbcj);  // core.cpp:166
+    }
+    __syncwarp();
+    if (jstar >= 0) {  // core.cpp:172-173: the particle's best fields, which the commit above just set to this candidate
+      const Cand cd = cand[jstar];  // (cost < gbest_cost <= pbest_cost_j for every j < P, an invariant of :137-140,:161-173)
+      gbc = cd.c;
+      gb0 = cd.x;
+      gb1 = cd.y;
+      gb2 = cd.th;
+      ++n_gb;
+    }
+    start = end;
+    if (start >= P) {
+      start = 0;
+      ++it;
+    }
+    par ^= 1;
+    ++rounds;
+  }
+
+  if (threadIdx.x == 0) {
+    out[0] = gb0;
+    out[1] = gb1;
+    out[2] = gb2;
+    out[3] = gbc;
+    if (stats) {
+      stats[0] = rounds;
+      stats[1] = n_gb;
+      stats[2] = 0;
+      stats[3] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Staging: points + compact table -> shared memory with bulk TMA; builds the cost evaluators.
 // ------------------------------------------------------------------------------------------
 struct Staged {
@@ -791,7 +938,15 @@ __global__ void __launch_bounds__(NW * 32) pso_kernel(const DevProblem* __restri
   const Staged st = stage_problem(pr, mp, sm.dyn, prm.smem_bytes - sm.fixed_bytes, sm.etab, sm.bar);
   double* o = out + 4 * (size_t)b;
   int* s = stats ? stats + kStatsWords * (size_t)b : nullptr;
-  if (st.mode == COST_FAST_GEOM) {
+  if (prm.variant == 1) {
+    if (st.mode == COST_FAST_GEOM) {
+      glir_body<CostOf<COST_FAST_GEOM>, NW>(CostOf<COST_FAST_GEOM>{st.fast}, pr, prm, sm, o, s);
+    } else if (st.mode == COST_FAST_ANY) {
+      glir_body<CostOf<COST_FAST_ANY>, NW>(CostOf<COST_FAST_ANY>{st.fast}, pr, prm, sm, o, s);
+    } else {
+      glir_body<CostOf<COST_SLOW>, NW>(CostOf<COST_SLOW>{st.slow}, pr, prm, sm, o, s);
+    }
+  } else if (st.mode == COST_FAST_GEOM) {
     pso_body<CostOf<COST_FAST_GEOM>, NW>(CostOf<COST_FAST_GEOM>{st.fast}, pr, prm, sm, o, s);
   } else if (st.mode == COST_FAST_ANY) {
     pso_body<CostOf<COST_FAST_ANY>, NW>(CostOf<COST_FAST_ANY>{st.fast}, pr, prm, sm, o, s);

@@ -45,6 +45,7 @@ def load_library():
     L.ndtpso_frame_point_count.argtypes = [C.c_void_p]
     L.ndtpso_frame_point_count.restype = C.c_int64
     L.ndtpso_frame_align.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_double)]
+    L.ndtpso_frame_glir.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ndtpso_frame_align_conf.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(capi.PsoConfig), C.POINTER(C.c_double)]
     L.ndtpso_frame_cost.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ndtpso_frame_add_pose.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
@@ -60,7 +61,7 @@ def load_library():
 #: every symbol include/ndtpso_frames.h declares
 EXPORTS = ["ndtpso_frame_new", "ndtpso_frame_free", "ndtpso_frame_load_laser", "ndtpso_frame_update", "ndtpso_frame_build",
            "ndtpso_frame_is_built", "ndtpso_frame_map_view", "ndtpso_frame_sparse_map_view", "ndtpso_frame_scan_points",
-           "ndtpso_frame_point_count", "ndtpso_frame_add_pose", "ndtpso_frame_dump_map", "ndtpso_frame_align", "ndtpso_frame_align_conf", "ndtpso_frame_cost", "ndtpso_frame_last_cost",
+           "ndtpso_frame_point_count", "ndtpso_frame_add_pose", "ndtpso_frame_dump_map", "ndtpso_frame_align", "ndtpso_frame_align_conf", "ndtpso_frame_glir", "ndtpso_frame_cost", "ndtpso_frame_last_cost",
            "ndtpso_frame_last_error"]
 
 
@@ -148,6 +149,14 @@ class Frame:
             rc = self.lib.ndtpso_frame_align(self.h, _d3(guess), new_frame.h, pose)
         else:
             rc = self.lib.ndtpso_frame_align_conf(self.h, _d3(guess), new_frame.h, C.byref(conf), pose)
+        if rc != 0:
+            raise capi.NdtpsoError(rc, (self.lib.ndtpso_frame_last_error() or b"").decode())
+        return np.array(list(pose))
+
+    def glir(self, guess, new_frame: "Frame", iterations: int = 50, deviation=(0., 0., 0.)) -> np.ndarray:
+        """glir_pso_optimization(guess, this, new_frame, iterations, deviation) of the drop-in library (core.h:21-23)."""
+        pose = (C.c_double * 3)()
+        rc = self.lib.ndtpso_frame_glir(self.h, _d3(guess), new_frame.h, int(iterations), _d3(deviation), pose)
         if rc != 0:
             raise capi.NdtpsoError(rc, (self.lib.ndtpso_frame_last_error() or b"").decode())
         return np.array(list(pose))

@@ -25,6 +25,11 @@ using std::vector;
 Vector3d pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* const new_frame,
                           const Array3d& deviation = {0, 0, 0}, const PSOConfig& pso_conf = PSOConfig());
 
+// The GLIR-PSO variant with its reference signature (core.h:21-23, core.cpp:118-186; the reference never calls it).  As
+// there: population PSO_POPULATION_SIZE, 3(P + 2) + 6PI draws of std::rand(), made on the host in the same order.
+Vector3d glir_pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, NDTFrame* new_frame, unsigned int iters_num = 50,
+                               const Array3d& deviation = {0, 0, 0});
+
 double cost_function(Vector3d trans, NDTFrame* const ref_frame, const NDTFrame* const new_frame);
 
 // best cost of the most recent pso_optimization call (the reference only prints it, core.cpp:111-114)

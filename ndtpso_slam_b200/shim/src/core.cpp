@@ -47,8 +47,9 @@ void fill_problem(ndtpso_problem* p, NDTFrame* ref_frame, const NDTFrame* new_fr
 
 }  // namespace
 
-Vector3d pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* const new_frame, const Array3d& deviation,
-                          const PSOConfig& pso_conf) {
+namespace {
+
+Vector3d solve(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* new_frame, const Array3d& deviation, const ndtpso_pso_config& cf) {
   ndtpso_ctx* ctx = context();
   ndtpso_problem p;
   fill_problem(&p, ref_frame, new_frame);
@@ -56,16 +57,7 @@ Vector3d pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, const NDT
     p.guess[k] = initial_guess[k];
     p.deviation[k] = deviation[k];
   }
-  ndtpso_pso_config cf;
-  cf.iterations = pso_conf.iterations;
-  cf.population = pso_conf.populationSize;
-  cf.num_threads = pso_conf.num_threads;
-  cf.reserved = 0;
-  cf.w = pso_conf.coeff.w;
-  cf.c1 = pso_conf.coeff.c1;
-  cf.c2 = pso_conf.coeff.c2;
-  cf.w_dumping = pso_conf.coeff.w_dumping;
-  // the reference's random numbers: the next 3 + 3P + 6PI outputs of the process-global std::rand()
+  // the reference's random numbers: the next 3 + 3P + 6PI (GLIR: 3(P + 2) + 6PI) outputs of the process-global std::rand()
   const int64_t n = ndtpso_rand_draws(&cf);
   std::vector<int32_t> stream(static_cast<size_t>(n));
   for (auto& r : stream) r = std::rand();
@@ -75,6 +67,31 @@ Vector3d pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, const NDT
   check(ndtpso_align_batch(ctx, 1, &p, &cf, pose, &cost), "ndtpso_align_batch");
   g_last_cost = cost;
   return Vector3d(pose[0], pose[1], pose[2]);
+}
+
+}  // namespace
+
+Vector3d pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* const new_frame, const Array3d& deviation,
+                          const PSOConfig& pso_conf) {
+  ndtpso_pso_config cf;
+  cf.iterations = pso_conf.iterations;
+  cf.population = pso_conf.populationSize;
+  cf.num_threads = pso_conf.num_threads;
+  cf.variant = NDTPSO_VARIANT_PSO;
+  cf.w = pso_conf.coeff.w;
+  cf.c1 = pso_conf.coeff.c1;
+  cf.c2 = pso_conf.coeff.c2;
+  cf.w_dumping = pso_conf.coeff.w_dumping;
+  return solve(initial_guess, ref_frame, new_frame, deviation, cf);
+}
+
+Vector3d glir_pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, NDTFrame* new_frame, unsigned int iters_num, const Array3d& deviation) {
+  ndtpso_pso_config cf;
+  ndtpso_pso_config_default(&cf);
+  cf.iterations = static_cast<int32_t>(iters_num);
+  cf.population = PSO_POPULATION_SIZE;  // core.cpp:134,145
+  cf.variant = NDTPSO_VARIANT_GLIR;
+  return solve(initial_guess, ref_frame, new_frame, deviation, cf);
 }
 
 double cost_function(Vector3d trans, NDTFrame* const ref_frame, const NDTFrame* const new_frame) {

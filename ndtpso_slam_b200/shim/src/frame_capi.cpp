@@ -86,6 +86,16 @@ int ndtpso_frame_align_conf(ndtpso_frame* ref_frame, const double* guess, ndtpso
     out_pose[2] = p.z();
   });
 }
+int ndtpso_frame_glir(ndtpso_frame* ref_frame, const double* guess, ndtpso_frame* new_frame, unsigned int iterations, const double* deviation,
+                      double* out_pose) {
+  return guarded([&]() {
+    const Vector3d p = glir_pso_optimization(Vector3d(guess[0], guess[1], guess[2]), &ref_frame->frame, &new_frame->frame, iterations,
+                                             Array3d(deviation[0], deviation[1], deviation[2]));
+    out_pose[0] = p.x();
+    out_pose[1] = p.y();
+    out_pose[2] = p.z();
+  });
+}
 int ndtpso_frame_cost(ndtpso_frame* ref_frame, ndtpso_frame* new_frame, const double* pose, double* out_cost) {
   return guarded([&]() { *out_cost = cost_function(Vector3d(pose[0], pose[1], pose[2]), &ref_frame->frame, &new_frame->frame); });
 }

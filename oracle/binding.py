@@ -68,6 +68,10 @@ class Oracle:
         self.lib.orc_pso.argtypes = [C.POINTER(OrcProblem), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(OrcConfig),
                                      C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(OrcStats)]
+        self.lib.orc_glir.restype = C.c_int
+        self.lib.orc_glir.argtypes = [C.POINTER(OrcProblem), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int,
+                                      C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(OrcStats)]
         self.lib.orc_rand_stream.argtypes = [C.c_uint32, C.POINTER(C.c_int32), C.c_int]
         self.lib.orc_align.restype = C.c_int
         self.lib.orc_align.argtypes = [C.POINTER(OrcAlignState), C.POINTER(OrcProblem), C.POINTER(C.c_double), C.c_uint32,
@@ -120,6 +124,24 @@ class Oracle:
         rc = self.lib.orc_pso(C.byref(p), _dp(guess), _dp(dev), C.byref(cf), int(seed), sp, _dp(pose), C.byref(cost), C.byref(st))
         if rc != 0:
             raise RuntimeError("orc_pso failed")
+        return pose, cost.value, {"gbest_updates": st.gbest_updates, "pbest_updates": st.pbest_updates, "rand_draws": st.rand_draws}
+
+    def glir(self, flat, guess, deviation, population, iterations, seed=1, stream=None):
+        """glir_pso_optimization (core.cpp:118-186); the reference's population is 30."""
+        p, _keep = self.problem(flat)
+        guess = np.ascontiguousarray(guess, dtype=np.float64)
+        dev = np.ascontiguousarray(deviation, dtype=np.float64)
+        pose = np.empty(3, dtype=np.float64)
+        cost = C.c_double(0.0)
+        st = OrcStats()
+        sp = None
+        if stream is not None:
+            stream = np.ascontiguousarray(stream, dtype=np.int32)
+            sp = stream.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = self.lib.orc_glir(C.byref(p), _dp(guess), _dp(dev), int(population), int(iterations), int(seed), sp, _dp(pose),
+                               C.byref(cost), C.byref(st))
+        if rc != 0:
+            raise RuntimeError("orc_glir failed")
         return pose, cost.value, {"gbest_updates": st.gbest_updates, "pbest_updates": st.pbest_updates, "rand_draws": st.rand_draws}
 
 
@@ -201,6 +223,8 @@ class Reference:
         L.ref_pso.restype = C.c_double
         L.ref_pso.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int,
                               C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_uint, C.POINTER(C.c_double)]
+        L.ref_glir.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_uint,
+                               C.POINTER(C.c_double)]
         L.ref_align.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_double)]
         L.ref_omp_max_threads.restype = C.c_int
         L.ref_sizeof_cell.restype = C.c_int
@@ -226,6 +250,14 @@ class Reference:
         secs = self.lib.ref_pso(ref_frame.h, cur.h, _dp(g), _dp(d), int(population), int(iterations), int(num_threads),
                                 w, c1, c2, w_dumping, int(bool(use_seed)), int(seed), _dp(pose))
         return pose, secs
+
+    def glir(self, ref_frame: RefFrame, cur: RefFrame, guess, deviation, iterations, seed=1, use_seed=True):
+        """glir_pso_optimization (core.cpp:118-186), population PSO_POPULATION_SIZE = 30."""
+        g = np.ascontiguousarray(guess, dtype=np.float64)
+        d = np.ascontiguousarray(deviation, dtype=np.float64)
+        pose = np.empty(3, dtype=np.float64)
+        self.lib.ref_glir(ref_frame.h, cur.h, _dp(g), _dp(d), int(iterations), int(bool(use_seed)), int(seed), _dp(pose))
+        return pose
 
     def align(self, ref_frame: RefFrame, guess, cur: RefFrame):
         g = np.ascontiguousarray(guess, dtype=np.float64)

@@ -215,6 +215,102 @@ int orc_pso(const orc_problem* p, const double* guess, const double* deviation, 
   return 0;
 }
 
+/* glir_pso_optimization, core.cpp:118-186 (the reference marks it "UNTESTED" and never calls it), single-thread order.
+ * The reference hard-wires the population to PSO_POPULATION_SIZE (30, config.h:21); here it is a parameter.
+ *   :125      global_best is a Particle of its own, drawn with the CALLER's deviation (zero_devi, :122-123, is never used)
+ *   :132-141  P + 1 particles are constructed (3 draws and one cost evaluation each: 3(P + 2) draws in all); the one built in
+ *             pass i is particles[i + 1], the one compared with global_best is particles[i]: the last particle never
+ *             takes part, neither here nor in the iterations (j < P, :145)
+ *   :146      omega = 1.1 - gbest_cost / (pbest_average_j / (j + 1)), j + 1 an unsigned converted to double
+ *   :147      c1 = c2 = 1.0 + gbest_cost / pbest_cost_j
+ *   :148-157  per coordinate: two draws (Array2d::Random().abs(): x then y), best_ratio = pbest_j[k] / gbest[k],
+ *             v = omega*v + c1*rx*(best_ratio*pbest - x) + c2*ry*((1./best_ratio)*gbest - x); x += v
+ *   :161-174  pbest, pbest_average += pbest_cost, gbest (strict <, taken from the particle's best fields)
+ * out_cost = global_best.best_cost. */
+int orc_glir(const orc_problem* p, const double* guess, const double* deviation, int population, int iterations, uint32_t seed,
+             const int32_t* stream, double* out_pose, double* out_cost, orc_stats* stats) {
+  const int P = population, I = iterations;
+  orc_rng g;
+  int drawn = 0;
+  if (!stream) orc_srand(&g, seed);
+#define NEXT_RAND() (stream ? stream[drawn++] : (drawn++, orc_rand(&g)))
+  const size_t n = (size_t)P + 1;
+  double* x = (double*)malloc(sizeof(double) * 3 * n);
+  double* v = (double*)malloc(sizeof(double) * 3 * n);
+  double* pb = (double*)malloc(sizeof(double) * 3 * n);
+  double* pbc = (double*)malloc(sizeof(double) * n);
+  double* cst = (double*)malloc(sizeof(double) * n);
+  double* pavg = (double*)malloc(sizeof(double) * n);
+  if (!x || !v || !pb || !pbc || !cst || !pavg) return -1;
+
+  double gb[3], gbc;
+  for (int k = 0; k < 3; ++k) gb[k] = guess[k] + orc_unit(NEXT_RAND()) * deviation[k]; /* :125 */
+  gbc = orc_cost(p, gb);
+#define NEW_PARTICLE(j)                                                                \
+  do {                                                                                 \
+    for (int k = 0; k < 3; ++k) {                                                      \
+      x[3 * (j) + k] = guess[k] + orc_unit(NEXT_RAND()) * deviation[k];                \
+      v[3 * (j) + k] = 0.;                                                             \
+      pb[3 * (j) + k] = x[3 * (j) + k];                                                \
+    }                                                                                  \
+    cst[j] = pbc[j] = pavg[j] = orc_cost(p, x + 3 * (j)); /* core.cpp:18-22 */         \
+  } while (0)
+  NEW_PARTICLE(0); /* :132 */
+  for (int i = 0; i < P; ++i) { /* :134-141 */
+    NEW_PARTICLE(i + 1);
+    if (cst[i] < gbc) {
+      gbc = pbc[i];
+      memcpy(gb, pb + 3 * i, sizeof gb);
+    }
+  }
+#undef NEW_PARTICLE
+
+  int n_gb = 0, n_pb = 0;
+  for (int it = 0; it < I; ++it) { /* :143-177 */
+    for (int j = 0; j < P; ++j) {
+      const double omega = 1.1 - gbc / (pavg[j] / (double)(unsigned)(j + 1));
+      const double c12 = 1.0 + gbc / pbc[j];
+      for (int k = 0; k < 3; ++k) {
+        const double rx = fabs(orc_unit(NEXT_RAND()));
+        const double ry = fabs(orc_unit(NEXT_RAND()));
+        const double best_ratio = pb[3 * j + k] / gb[k];
+        v[3 * j + k] = omega * v[3 * j + k] + c12 * rx * (best_ratio * pb[3 * j + k] - x[3 * j + k]) +
+                       c12 * ry * ((1. / best_ratio) * gb[k] - x[3 * j + k]);
+        x[3 * j + k] = x[3 * j + k] + v[3 * j + k];
+      }
+      cst[j] = orc_cost(p, x + 3 * j);
+      if (cst[j] < pbc[j]) {
+        pbc[j] = cst[j];
+        memcpy(pb + 3 * j, x + 3 * j, 3 * sizeof(double));
+        ++n_pb;
+      }
+      pavg[j] += pbc[j];
+      if (cst[j] < gbc) {
+        gbc = pbc[j];
+        memcpy(gb, pb + 3 * j, sizeof gb);
+        ++n_gb;
+      }
+    }
+  }
+#undef NEXT_RAND
+
+  memcpy(out_pose, gb, sizeof gb);
+  if (out_cost) *out_cost = gbc;
+  if (stats) {
+    stats->gbest_updates = n_gb;
+    stats->pbest_updates = n_pb;
+    stats->rand_draws = drawn;
+    stats->_pad = 0;
+  }
+  free(x);
+  free(v);
+  free(pb);
+  free(pbc);
+  free(cst);
+  free(pavg);
+  return 0;
+}
+
 /* NDTFrame::align, ndtframe.cpp:251-266: the deviation rule and the s_* bookkeeping
  * around pso_optimization (which it calls with the DEFAULT PSOConfig: 30 x 50,
  * w=.8, c1=c2=2, w_dumping=1; config.h:20-37).  state = {s_iter, s_prev_pose[3], s_pose_diff[3]}. */

@@ -165,6 +165,18 @@ void ref_align(void* ref, const double* guess, void* cur, double* out_pose) {
   out_pose[2] = p.z();
 }
 
+// glir_pso_optimization (core.cpp:118-186, "UNTESTED" in the reference; population fixed to PSO_POPULATION_SIZE).
+void ref_glir(void* ref, void* cur, const double* guess, const double* dev, int iterations, int use_seed, unsigned seed, double* out_pose) {
+  NDTFrame* r = static_cast<NDTFrame*>(ref);
+  if (!r->built) r->build();
+  if (use_seed) std::srand(seed);
+  Vector3d p = glir_pso_optimization(Vector3d(guess[0], guess[1], guess[2]), r, static_cast<NDTFrame*>(cur),
+                                     static_cast<unsigned>(iterations), Array3d(dev[0], dev[1], dev[2]));
+  out_pose[0] = p.x();
+  out_pose[1] = p.y();
+  out_pose[2] = p.z();
+}
+
 int ref_omp_max_threads(void) { return omp_get_max_threads(); }
 
 int ref_sizeof_cell(void) { return static_cast<int>(sizeof(NDTCell)); }

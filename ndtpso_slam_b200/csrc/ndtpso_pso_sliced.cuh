@@ -85,7 +85,7 @@ struct SlicedSmem {
   double* pb;       // [P][3]
   double* pbc;      // [P]
   // fp32 screening (CL == 1 only; null when off)
-  float4* pose32;   // [P+1] {x, y, cos, sin} of the current round's candidates
+  float4* pose32;   // [P+1][2] {x, y, cos, sin}, {-sin, cos, 0, 0} of the current round's candidates (the register pairs the packed transform takes)
   float* lbpart;    // [(P+1)*NW] per-warp partial sums of the upper bounds
   int* surv;        // [P+2] candidates that need the fp64 evaluation; surv[P+1] = their number
   float* rec32;     // [(n_rec+1)][8] {h00, h01, h11, hs, mx, my, -, -}
@@ -104,7 +104,7 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
 }
 // shared memory of the fp32 screen without its record table: pose32, lbpart, surv
 __host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
-  return (P + 1) * 16 + round16((P + 1) * NW * 4) + round16((P + 2) * 4);
+  return (P + 1) * 32 + round16((P + 1) * NW * 4) + round16((P + 2) * 4);
 }
 // total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2).  With the screen (screen_recs > 0:
 // the largest record count of the batch, null record included) the fp32 records take screen_recs * 32 bytes more.
@@ -144,7 +144,7 @@ __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, i
   if (screen) {
     p = base + kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP);
     s.pose32 = reinterpret_cast<float4*>(p);
-    p += (P + 1) * 16;
+    p += (P + 1) * 32;
     s.lbpart = reinterpret_cast<float*>(p);
     p += round16((P + 1) * PW * 4);
     s.surv = reinterpret_cast<int*>(p);
@@ -342,7 +342,10 @@ constexpr int kScreenMagicBits = 0x4B400000;     // its bit pattern
 __device__ __forceinline__ void screen_point(const ScreenCtx& m, const float2 px2, const float2 py2, const float2 txy, const float2 cs,
                                              const float2 sc, float& acc) {
   const float2 xy = __ffma2_rn(px2, cs, __ffma2_rn(py2, sc, txy));  // transform_point
-  const bool inb = fmaxf(fabsf(xy.x), fabsf(xy.y)) < m.x_max;       // square frames only; trusted away from the cell edges
+  // No bounds test: a point outside the frame contributes 0 to the fp64 cost, so ANY e >= 0 bounds its term.  Outside in y
+  // its index leaves the strip and clamps to the null record; outside in x it aliases to a cell of a neighbouring row, a
+  // frame width away, whose Gaussian is 0 there to fp32 (d is taken from the true position).  Points that fp32 and fp64
+  // place on different sides of the frame's border lie within beta of a cell edge (frames are whole cells): `unc` below.
   const float2 uv = __ffma2_rn(xy, m.k2, m.off2);                   // cell coordinates - 0.5
   const float2 t2 = __fadd2_rn(uv, make_float2(kScreenMagic, kScreenMagic));  // round to nearest of (u - 0.5) = floor(u), |u| < 2^22
   const float2 fl = __fadd2_rn(t2, make_float2(-kScreenMagic, -kScreenMagic));
@@ -350,7 +353,7 @@ __device__ __forceinline__ void screen_point(const ScreenCtx& m, const float2 px
   const bool unc = fmaxf(fabsf(df.x), fabsf(df.y)) > m.beta_c;      // within beta of a cell edge
   // ix + gw*iy - base with ix = bits(t) - magic bits: the constants are folded into `base`
   const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y) - m.base;
-  const unsigned gs = inb ? min(g, static_cast<unsigned>(m.span)) : static_cast<unsigned>(m.span);
+  const unsigned gs = min(g, static_cast<unsigned>(m.span));
   const unsigned r = m.grid[gs];
   const float* q = m.rec32 + 8 * r;
   const float4 l = *reinterpret_cast<const float4*>(q);        // l00, l11, l10, kappa2
@@ -418,14 +421,17 @@ __device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&
                                              float* lbpart, int j, int hi, int NW, int warp, int lane) {
   float acc[JB];
   float4 ps[JB];
+  float2 sc2[JB];
 #pragma unroll
   for (int b = 0; b < JB; ++b) {
-    ps[b] = pose32[min(j + b, hi - 1)];
+    const float4* q = pose32 + 2 * min(j + b, hi - 1);
+    ps[b] = q[0];
+    sc2[b] = *reinterpret_cast<const float2*>(q + 1);
     acc[b] = 0.f;
   }
 #pragma unroll
   for (int b = 0; b < JB; ++b) {
-    const float2 txy = make_float2(ps[b].x, ps[b].y), cs = make_float2(ps[b].z, ps[b].w), sc = make_float2(-ps[b].w, ps[b].z);
+    const float2 txy = make_float2(ps[b].x, ps[b].y), cs = make_float2(ps[b].z, ps[b].w), sc = sc2[b];
 #pragma unroll
     for (int k = 0; k < NPT; ++k) screen_point(m, px2[k], py2[k], txy, cs, sc, acc[b]);
   }
@@ -672,7 +678,11 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
       double s, c;
       sincos(nx[2], &s, &c);
       pose[j] = Pose{nx[0], nx[1], c, s, nx[2], 0.};
-      if (CL == 1 && scr) sm.pose32[j] = make_float4(static_cast<float>(nx[0]), static_cast<float>(nx[1]), static_cast<float>(c), static_cast<float>(s));
+      if (CL == 1 && scr) {
+        const float cf = static_cast<float>(c), sf = static_cast<float>(s);
+        sm.pose32[2 * j] = make_float4(static_cast<float>(nx[0]), static_cast<float>(nx[1]), cf, sf);
+        sm.pose32[2 * j + 1] = make_float4(-sf, cf, 0.f, 0.f);
+      }
       sm.vnew[3 * j] = nv[0];
       sm.vnew[3 * j + 1] = nv[1];
       sm.vnew[3 * j + 2] = nv[2];
@@ -1026,7 +1036,9 @@ __global__ void __launch_bounds__(MAXT, 1) screen_bound_kernel(const DevProblem*
     const double* p = poses + 3 * ((size_t)b * m_poses + j);
     double s, c;
     sincos(p[2], &s, &c);
-    sm.pose32[j] = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(c), static_cast<float>(s));
+    const float cf = static_cast<float>(c), sf = static_cast<float>(s);
+    sm.pose32[2 * j] = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), cf, sf);
+    sm.pose32[2 * j + 1] = make_float4(-sf, cf, 0.f, 0.f);
   }
   __syncthreads();
   float2 px2[NPT], py2[NPT];

@@ -752,6 +752,9 @@ int try_cluster(ndtpso_batch* bt, bool forced) {
   return npt == 1 ? launch_sliced_cfg<1, 8, CL, 384, 1>(bt, nw, G, smem) : launch_sliced_cfg<2, 4, CL, 384, 1>(bt, nw, G, smem);
 }
 
+#ifndef NDTPSO_MINB3
+#define NDTPSO_MINB3 2  // CTAs per SM the 3-points-per-thread shape is compiled for (2 => 80 registers); tools/variant_time.py
+#endif
 int launch_sliced(ndtpso_batch* bt) {
   ndtpso_ctx* ctx = bt->ctx;
   if (!bt->all_compact || !bt->all_symmetric) return 1;
@@ -810,8 +813,8 @@ int launch_sliced(ndtpso_batch* bt) {
                                                                                         : launch_sliced_cfg<1, 4, 1, 640, 1>(bt, nw, 1, smem, scr);
     case 2: return jb == 1 ? launch_sliced_cfg<2, 1, 1, 640, 1>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<2, 2, 1, 640, 1>(bt, nw, 1, smem, scr)
                                                                                         : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem, scr);
-    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, 2>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, 2>(bt, nw, 1, smem, scr)
-                                                                                        : launch_sliced_cfg<3, 4, 1, 384, 2>(bt, nw, 1, smem, scr);
+    case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr)
+                                                                                        : launch_sliced_cfg<3, 4, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr);
     case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem, scr);
     case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
     default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem, scr);

@@ -175,3 +175,40 @@ def test_gpu_shim_chain(gz):
         guess = pose
     ref.close()
     q.close()
+
+
+@pytest.mark.gpu
+def test_gpu_device_frames_glir(ctx, reference):
+    """ndtpso_dframes_align with variant = GLIR on maps built on the device == the reference's glir_pso_optimization on its own maps
+    (align()'s deviation rule gives the first-call deviation the reference golden cases use)."""
+    from ndtpso_slam_b200 import capi, synthetic as syn
+    from ndtpso_slam_b200.dframes import DeviceFrames, RNG_SEEDED
+    cfg = syn.CFG1
+    s, S = cfg.sensor, cfg.map_size_m
+    n = 2
+    df = DeviceFrames(ctx, n, S, S, cfg.cell_side, s.beams)
+    refs, queries, guesses = [], [], []
+    for b in range(n):
+        ss = syn.trajectory_problem(cfg, b)
+        rf = reference.frame(width=S, height=S, cell_side=cfg.cell_side, init_windows=True)
+        refs.append(rf)
+        for pose, ranges in ss.map_scans:
+            f = reference.frame(width=S, height=S, cell_side=float(S), init_windows=False)
+            f.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+            rf.update(pose, f)
+            pts = [f.flatten_points() if j == b else np.zeros((0, 2)) for j in range(n)]
+            df.set_scan_points(pts)
+            df.update([pose if j == b else (0., 0., 0.) for j in range(n)])
+        q = reference.frame(width=S, height=S, cell_side=float(S), init_windows=False)
+        q.load_laser(ss.query_ranges, s.angle_min, s.angle_increment, s.range_max)
+        queries.append(q)
+        guesses.append(ss.guess)
+    df.set_scan_points([q.flatten_points() for q in queries])
+    conf = capi.PsoConfig.make(population=30, iterations=25, variant=capi.VARIANT_GLIR)
+    seeds = [21, 22]
+    pose, cost = df.align(guesses, conf, RNG_SEEDED, seeds)
+    for b in range(n):
+        want = reference.glir(refs[b], queries[b], guesses[b], syn.DEFAULT_DEVIATION, 25, seed=seeds[b])
+        assert np.abs(pose[b] - want).max() <= POSE_ATOL, (b, pose[b], want)
+        assert rel_err(cost[b], reference.cost(refs[b], queries[b], want)) <= SCORE_RTOL
+    df.close()

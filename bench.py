@@ -12,7 +12,7 @@ its own dense (mu, Sigma^-1, built) table.
              of the batch alternate on two streams so that consecutive steps overlap; CUDA events around the K steps
   single_stream  the same with one copy on one stream, L2 flushed between steps (per-step events)
   e2e        the same metric through ndtpso_align_submit/collect with HOST buffers (pinned): H2D of every
-             input + kernels + D2H of the poses inside the timed region, two batches in flight
+             input + kernels + D2H of the poses inside the timed region, three batches in flight (--e2e-depth)
   tracking   the reference's whole per-scan callback (loadLaser -> align -> update) on device-resident maps
   roofline   dominant kernel (pso_sliced_kernel): algorithmic bytes / its duration vs the measured HBM peak;
              the fp64 pipe fraction beside it (the bound that really binds)
@@ -22,6 +22,7 @@ its own dense (mu, Sigma^-1, built) table.
 `--impl reference` times only the CPU arm, same metric/config.
 """
 import argparse
+import collections
 import json
 import multiprocessing as mp
 import os
@@ -483,24 +484,31 @@ def _run_gpu_arm(args, real_stdout):
     stats = bts[0].stats()
 
     # ---- e2e arm: host buffers in, host poses out, every step.  Throughput form of the public API:
-    # ndtpso_align_submit (stage + H2D + launches) / ndtpso_align_collect (D2H + sync), two batches in
+    # ndtpso_align_submit (stage + H2D + launches) / ndtpso_align_collect (D2H + sync), several batches in
     # flight so the host stages step k+1 while the GPU solves step k.  Every step moves its own inputs
     # host->device and its own poses device->host.  The one-call synchronous form is timed beside it.
     ctx.set_stream(0)
     for _ in range(max(1, args.warmup // 2)):
         ctx.align_batch(pset, conf)
-    ticket = ctx.align_submit(pset, conf)  # warm-up of the two-in-flight form (second set of arenas)
-    nxt = ctx.align_submit(pset, conf)
-    ctx.align_collect(ticket)
-    ctx.align_collect(nxt)
+    depth = max(1, args.e2e_depth)
+
+    def e2e_steps(n):
+        # `depth` batches in flight: with two, the GPU holds a single batch while the host stages and uploads the next one
+        # (0.6 + 0.3 ms of every 2.2 ms step: 117 k matches/s); with three it always has two batches queued on its two
+        # streams and the end-to-end rate equals the resident one (tools/e2e_depth.py)
+        tickets, out = collections.deque(), None
+        for _ in range(n):
+            tickets.append(ctx.align_submit(pset, conf))
+            if len(tickets) >= depth:
+                out = ctx.align_collect(tickets.popleft())
+        while tickets:
+            out = ctx.align_collect(tickets.popleft())
+        return out
+
+    e2e_steps(2 * depth)  # warm-up of the in-flight form (one set of arenas per batch in flight)
     barrier()
     t0 = time.perf_counter()
-    ticket = ctx.align_submit(pset, conf)
-    for _ in range(args.steps - 1):
-        nxt = ctx.align_submit(pset, conf)
-        ep, ec = ctx.align_collect(ticket)
-        ticket = nxt
-    ep, ec = ctx.align_collect(ticket)
+    ep, ec = e2e_steps(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -567,7 +575,7 @@ def _run_gpu_arm(args, real_stdout):
                        "pipelining": "step k runs on copy k % 4 and stream k & 1, so consecutive steps overlap while one drains",
                        "collective": exchange_kind},
             "e2e": {"value": e2e, "unit": "scan-matches/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                    "api": "ndtpso_align_submit/collect, 2 batches in flight",
+                    "api": f"ndtpso_align_submit/collect, {depth} batches in flight",
                     "one_call_sync": world * B * args.steps / e2e_sync_s},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -610,7 +618,8 @@ def main():
     ap.add_argument("--ref-matches", type=int, default=4, help="CPU arm: matches per host worker per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tracking", action="store_true", help="skip the device-resident tracking leg")
-    ap.add_argument("--tracking-groups", type=int, default=2, help="tracking leg: independent groups of robots served by their own host thread and stream")
+    ap.add_argument("--tracking-groups", type=int, default=3, help="tracking leg: independent groups of robots served by their own host thread and stream")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="e2e arm: batches kept in flight through ndtpso_align_submit/collect")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N > 1: how the solved poses reach every rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

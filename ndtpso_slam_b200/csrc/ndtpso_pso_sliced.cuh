@@ -310,6 +310,8 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //   * Cell.  If the fp32 point lies within beta cell sides of a cell edge (which includes the frame's border: frames are
 //     whole cells), fp32 and fp64 may disagree on the cell: the point counts as the worst case, exp(.) = 1.  Otherwise both
 //     pick the same cell c, and |d_k| <= dmax_k(c), the distance from the mean to the far side of the cell.
+//     A point outside the frame has the term 0 in fp64, so whatever e >= 0 the screen computes for it bounds it: there is no
+//     bounds test (screen_point), and the error terms below, derived for a point inside its cell, need not hold for it.
 //   * Exponent.  With d = d* + eps, |eps_k| <= delta_d, and Cauchy-Schwarz + AM-GM on the cross term,
 //         A(d*) >= (1 - t) A(d) - A(eps)/t,          A(eps) <= hs delta_d^2,   hs = H00 + 2|H01| + H11.
 //     A(d) = z0^2 + z1^2 with z = L'd (Cholesky factor L of H).  In fp32 (factor rounded, two FMAs) each z_k is off by at
@@ -327,7 +329,6 @@ struct ScreenCtx {
   const float* rec32;          // shared: [n_rec + 1][8] = {l00, l11, l10, kappa2, -mx, -my, -, -}
   const unsigned short* grid;  // shared
   float2 k2, off2;  // (1/cs, 1/cs) and ((W/2)/cs - 0.5, (H/2)/cs - 0.5): the cell coordinates minus one half
-  float x_max;      // square frames: x_max == y_max
   float beta_c;     // 0.5 - beta
   int gw, span;
   unsigned base;
@@ -966,7 +967,6 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
     }
     sc->rec32 = sm.rec32;
     sc->grid = m.grid;
-    sc->x_max = static_cast<float>(mp.x_max);
     sc->k2 = make_float2(static_cast<float>(mp.inv_cs), static_cast<float>(mp.inv_cs));
     sc->off2 = make_float2(static_cast<float>(mp.hw * mp.inv_cs - 0.5), static_cast<float>(mp.hh * mp.inv_cs - 0.5));
     sc->beta_c = prm->scr_beta_c;

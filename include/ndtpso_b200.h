@@ -129,7 +129,7 @@ enum {
   NDTPSO_OPT_KERNEL = 4,        /* 0 = auto, 1 = warp-per-particle (generic), 2 = point-sliced */
   NDTPSO_OPT_POINTS_PER_THREAD = 5, /* point-sliced kernel: scan points held per thread; 0 = auto */
   NDTPSO_OPT_CANDIDATE_BATCH = 6,  /* point-sliced kernel: candidates scored together (1, 2, 4); 0 = auto */
-  NDTPSO_OPT_PIPELINE_CHUNKS = 7,  /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4, default 1) */
+  NDTPSO_OPT_PIPELINE_CHUNKS = 7,  /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4; default 0 = auto: 3 from 128 problems on) */
   NDTPSO_OPT_EXCHANGE_TIMEOUT_MS = 8, /* ndtpso_exchange_wait: give up after this long (default 10000) */
   NDTPSO_OPT_HOT_CHUNK = 9, /* point-sliced kernel: particles speculated per round while gbest improves often; -1 auto, 0 = whole swarm */
   NDTPSO_OPT_SCREEN = 10    /* point-sliced kernel: fp32 lower-bound screen before the fp64 cost (results identical either way); -1 auto, 0 off */

@@ -7,6 +7,8 @@
 // small pool in the context, so a steady stream of align calls performs no cudaMalloc.
 #include "../../include/ndtpso_b200.h"
 
+#include <sched.h>
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -58,7 +60,7 @@ struct ndtpso_ctx {
   int opt_cluster = 0;
   int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
-  int opt_chunks = 1;      // pipelined align_batch: number of chunks (1 = off)
+  int opt_chunks = 0;      // pipelined align_batch: number of chunks (1 = off, 0 = auto: 3 from 128 problems on)
   int opt_screen = -1;     // fp32 screening of the sliced kernel: -1 auto (on when the batch qualifies), 0 off, 1 on when it qualifies
   int opt_hot_chunk = -1;  // speculation window of the sliced kernel while gbest improves often: -1 auto, 0 off
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
@@ -248,8 +250,17 @@ class HostPool {
 
  private:
   HostPool() {
-    const int hw = (int)std::thread::hardware_concurrency();
-    const int nw = std::max(0, std::min(7, hw - 1));
+    // Threads this process may use for staging: the cores it may run on, divided by the ranks sharing the host (torchrun
+    // exports LOCAL_WORLD_SIZE: eight ranks of eight threads each on a 32-core host only queue behind one another), at most
+    // 8 with the caller.  NDTPSO_HOST_THREADS overrides.
+    int hw = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
+    int share = 1;
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) share = std::max(1, std::atoi(e));
+    int budget = std::max(1, hw / share);
+    if (const char* e = std::getenv("NDTPSO_HOST_THREADS")) budget = std::max(1, std::min(64, std::atoi(e)));
+    const int nw = std::max(0, std::min(7, budget - 1));
     for (int t = 0; t < nw; ++t) workers_.emplace_back([this] { loop(); });
   }
   ~HostPool() {
@@ -992,7 +1003,7 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
       ctx->opt_kernel = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_PIPELINE_CHUNKS:
-      if (value < 1 || value > 4) return fail(ctx, NDTPSO_ERR_ARG, "pipeline chunks must be in 1..4");
+      if (value < 0 || value > 4) return fail(ctx, NDTPSO_ERR_ARG, "pipeline chunks must be in 0..4 (0 = auto)");
       ctx->opt_chunks = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_CANDIDATE_BATCH:
@@ -1181,7 +1192,10 @@ int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problem
   // each staged (host scan + pack of the built cells), uploaded and launched on its own stream, so
   // the host stages chunk k+1 while the GPU already works on chunk k.  Results are identical to the
   // one-shot path (a problem's result does not depend on the batch it is in).
-  const int chunks = (ctx->stream == ctx->own_stream && n >= 64) ? std::min(ctx->opt_chunks, n / 32) : 1;
+  // auto: three chunks from 128 problems on (tools/onecall_chunks.py, one B200, cfg2: 128 problems 2.71 -> 2.36 ms per call,
+  // 256: 3.91 -> 3.21, 512: 6.84 -> 5.71; no difference at 64)
+  const int want = ctx->opt_chunks > 0 ? ctx->opt_chunks : (n >= 128 ? 3 : 1);
+  const int chunks = (ctx->stream == ctx->own_stream && n >= 64) ? std::min(want, n / 32) : 1;
   if (chunks <= 1) {
     ndtpso_batch* bt = nullptr;
     int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // built cells only cross PCIe

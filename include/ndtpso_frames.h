@@ -25,6 +25,9 @@ void ndtpso_frame_load_laser(ndtpso_frame* f, const float* ranges, int n, float 
 void ndtpso_frame_update(ndtpso_frame* f, const double* pose /* [3] */, ndtpso_frame* new_frame);
 /* NDTFrame::build (ndtframe.cpp:68) */
 void ndtpso_frame_build(ndtpso_frame* f);
+/* NDTFrame::resetCells (ndtframe.cpp:208-212): drops every cell's points and window statistics; mean, Sigma^-1 and the
+ * built flags stay as they are, like in the reference */
+void ndtpso_frame_reset_cells(ndtpso_frame* f);
 int ndtpso_frame_is_built(const ndtpso_frame* f);
 /* the table cost_function reads: dense (one row per cell) or sparse (built cells only, after build) */
 void ndtpso_frame_map_view(const ndtpso_frame* f, ndtpso_map_view* out);

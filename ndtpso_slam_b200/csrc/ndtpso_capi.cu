@@ -654,26 +654,27 @@ int launch_pso(ndtpso_batch* bt, int smem) {
 // time; a problem may be spread over a cluster of CL CTAs (G candidate groups x S point slices).
 // launch_sliced returns 1 when the batch does not qualify (table too large for shared memory,
 // scan too long, > 65534 built cells, asymmetric Sigma^-1).
-// Constants of the fp32 screen's error bound for this batch (see ndtpso_pso_sliced.cuh); false = the batch does not qualify.
-//   dx: error of a transformed point's coordinate in fp32, x = fma(px, c, fma(-py, s, tx)) with every input rounded to fp32
-//       (u = 2^-24 relative each): to first order u (3|px c| + 4|py s| + 3|tx| + |x|).  For a point that ends up inside a frame
-//       |x| <= ext and |tx| <= ext + 1.42 pmax, so dx <= u (11.3 pmax + 4 ext) = 2^-23 (5.7 pmax + 2 ext); taken as
-//       2^-23 (8 pmax + 4 ext).
-//   dd: error of its offset from a cell mean: dx + rounding of the mean and of the subtraction (<= 2^-23 ext), times 1.25.
-//   beta: band around cell edges inside which fp32 and fp64 may pick different cells: 4x the error of the cell coordinate.
+// Constants of the fp32 screen's error bound for this batch (derivation: "fp32 screen" in ndtpso_pso_sliced.cuh); false = the
+// batch does not qualify.  Everything is in cell sides.
+//   du:   bound on |Uf - U*|, the fp32 error of a transformed point's cell coordinate, for every point the fp64 evaluation
+//         places inside its frame: first-order part 2^-24 (11.25 pmax + 3 W)/cs + 1.5 2^-24; taken as
+//         2^-24 (12 pmax' + 3.01 W)/cs + 2^-23 with pmax' = max(pmax, 1), which covers every higher-order term and the fp64
+//         side's own rounding as long as (pmax + W)/cs <= 2^22 (checked here).  pmax, W, 1/cs: the largest of the batch.
+//   beta: band around cell edges inside which fp32 and fp64 may pick different cells; it only has to be >= du, and is taken
+//         four times that, at least 5e-4.
 bool screen_params(const ndtpso_batch* bt, PsoParams* prm) {
   prm->screen = 0;
   const ndtpso_ctx* ctx = bt->ctx;
   if (ctx->opt_screen == 0 || !bt->scr_ok || !(bt->scr_pmax <= 1e6) || !(bt->scr_ext > 0.) || bt->scr_gw >= (1 << 20)) return false;
-  const double u23 = 1.1920928955078125e-07;  // 2^-23
-  const double pmax = std::max(bt->scr_pmax, 1.0), ext = bt->scr_ext;
-  const double dx = u23 * (8. * pmax + 4. * ext);
-  const double dd = 1.25 * (dx + u23 * ext);
-  const double du = dx * bt->scr_inv_cs + u23 * bt->scr_gw;
+  if (bt->max_n_rec + 1 > kScreenMaxRecords) return false;  // the staged grid holds 16-bit shared addresses of the screen's records
+  const double u24 = 5.9604644775390625e-08;  // 2^-24
+  const double pmax = std::max(bt->scr_pmax, 1.0), W = 2. * bt->scr_ext;
+  if ((pmax + W) * bt->scr_inv_cs > 4194304.) return false;
+  const double du = u24 * (12. * pmax + 3.01 * W) * bt->scr_inv_cs + 2. * u24;
   const double beta = std::max(5e-4, 4. * du);
   if (beta > 0.05) return false;
   prm->screen = 1;
-  prm->scr_dd2 = (float)(dd * dd * 1.000001);
+  prm->scr_du = (float)(du * 1.000001);  // rounded to fp32: 1e-6 relative covers the rounding
   prm->scr_beta_c = (float)(0.5 - beta);
   return true;
 }
@@ -721,6 +722,9 @@ constexpr int kSlicedMaxWarps[kSlicedMaxNPT + 1] = {0, 20, 20, 12, 10, 8, 8};
 // GPCs of a B200, so 16 problems are faster on clusters of 4) unless the size was forced.
 template <int CL>
 int try_cluster(ndtpso_batch* bt, bool forced) {
+#ifdef NDTPSO_DEV_FAST  // experiment builds (tools/variant_time.py): only the production shape is instantiated
+  return 1;
+#else
   ndtpso_ctx* ctx = bt->ctx;
   const int n = std::max(bt->max_pts, 1);
   const int S = std::min(CL, 4), G = CL / S;
@@ -759,6 +763,7 @@ int try_cluster(ndtpso_batch* bt, bool forced) {
     if (bt->n > max_clusters) return 1;
   }
   return npt == 1 ? launch_sliced_cfg<1, 8, CL, 384, 1>(bt, nw, G, smem) : launch_sliced_cfg<2, 4, CL, 384, 1>(bt, nw, G, smem);
+#endif
 }
 
 #ifndef NDTPSO_MINB3
@@ -817,6 +822,9 @@ int launch_sliced(ndtpso_batch* bt) {
   }
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;
+#ifdef NDTPSO_DEV_FAST
+  return npt == 3 ? launch_sliced_cfg<3, 4, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr) : npt == 4 ? launch_sliced_cfg<4, 4, 1, 320, 2>(bt, nw, 1, smem, scr) : 1;
+#else
   switch (npt) {
     case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 1, 640, 1>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<1, 2, 1, 640, 1>(bt, nw, 1, smem, scr)
                                                                                         : launch_sliced_cfg<1, 4, 1, 640, 1>(bt, nw, 1, smem, scr);
@@ -828,6 +836,7 @@ int launch_sliced(ndtpso_batch* bt) {
     case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
     default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
   }
+#endif
 }
 
 // Points the next PSO launch of `bt` at the gathered buffers of all ranks (next epoch), or switches publishing off.
@@ -1084,6 +1093,9 @@ int ndtpso_batch_solve(ndtpso_batch* bt) {
   }
   if (!bt->ev[0])
     for (auto& e : bt->ev) CUDA_TRY(ctx, cudaEventCreate(&e));
+  // the upload ran on the copy stream: whatever stream is current NOW (ndtpso_ctx_set_stream may have changed it since
+  // ndtpso_batch_create) must not start before it has finished
+  if (bt->ev_up) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, bt->ev_up, 0));
   CUDA_TRY(ctx, cudaEventRecord(bt->ev[0], ctx->stream));
   int rc = launch_compact(bt);
   if (rc) return rc;
@@ -1354,13 +1366,18 @@ int ndtpso_screen_bounds(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* probl
   unsigned char* d = static_cast<unsigned char*>(bt->dev.ptr);
   const double* d_poses = reinterpret_cast<const double*>(d + o_up);
   double* d_out = reinterpret_cast<double*>(d + o_dev);
+#ifdef NDTPSO_DEV_FAST
+  npt = 3;
+#endif
   switch (npt) {
+#ifndef NDTPSO_DEV_FAST
     case 1: rc = launch_screen_bound<1>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
     case 2: rc = launch_screen_bound<2>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
-    case 3: rc = launch_screen_bound<3>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
     case 4: rc = launch_screen_bound<4>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
     case 5: rc = launch_screen_bound<5>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
-    default: rc = launch_screen_bound<6>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+    case 6: rc = launch_screen_bound<6>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
+#endif
+    default: rc = launch_screen_bound<3>(bt, nw, smem, prm, n_poses, d_poses, d_out); break;
   }
   if (rc) return cleanup(rc);
   cudaError_t e = cudaMemcpyAsync(out_lower, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1478,7 +1495,11 @@ int ndtpso_exchange_results(ndtpso_exchange* ex, double* out_pose, double* out_c
   CUDA_TRY(ctx, cudaMemcpyAsync(ex->pin, ndtpso_exchange_device_results(ex), sizeof(double) * 4 * rows, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(&err, ex->base + ex->o_err, sizeof err, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (err) return fail(ctx, NDTPSO_ERR_CUDA, "exchange: rank " + std::to_string(err - 1) + " did not arrive within the time limit");
+  if (err) {
+    // report the timeout once: a peer that catches up later must not fail every following call
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->base + ex->o_err, 0, sizeof(int), ctx->stream));
+    return fail(ctx, NDTPSO_ERR_CUDA, "exchange: rank " + std::to_string(err - 1) + " did not arrive within the time limit");
+  }
   for (size_t i = 0; i < rows; ++i) {
     if (out_pose) {
       out_pose[3 * i] = ex->pin[4 * i];

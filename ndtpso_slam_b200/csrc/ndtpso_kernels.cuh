@@ -84,7 +84,7 @@ struct PsoParams {
   int hot_thresh;   // improvements in an iteration that keep the next one's window small
   // fp32 screening of the point-sliced kernel (ndtpso_pso_sliced.cuh): 0 = off
   int screen;
-  float scr_dd2;    // delta_d^2: square of the bound on the fp32 error of a transformed point's offset from a cell mean
+  float scr_du;     // bound on the fp32 error of a transformed point's cell coordinate, in cell sides (rounded up)
   float scr_beta_c; // 0.5 - beta: a point closer than beta cell sides to a cell edge counts as worst case
   PeerExchange ex;
 };

@@ -33,8 +33,8 @@ enum {
   VAR_PIN_CONSTS = 4,     // keep 16/ln2 and 1/7! in vector registers (loaded through a lane-dependent address) instead of
                           // re-materialising them from uniform registers with two moves per use: -4 instructions per evaluation
 };
-#ifndef NDTPSO_SCREEN_JB8
-#define NDTPSO_SCREEN_JB8 1  // the screen takes candidates eight at a time first (more loads in flight, fewer reductions): +2 %
+#ifndef NDTPSO_SCREEN_JB
+#define NDTPSO_SCREEN_JB 8  // candidates the screen takes at a time first (more loads in flight, fewer reductions), then 4, then pairs
 #endif
 #ifndef NDTPSO_PROD_VARIANT
 #define NDTPSO_PROD_VARIANT 4
@@ -61,50 +61,49 @@ struct __align__(16) Pose {
   double x, y, c, s, th, pad;  // {x, y} and {cos, sin} are the two 16-byte loads of phase B
 };
 
-// Shared memory: [mbarrier 16][exp table 128][exp constants 64][records][grid] at FIXED offsets
-// (so the hot loop's table addresses are a constant and one register), then the swarm arrays.
-#if (NDTPSO_PROD_VARIANT & 4)
-constexpr int kSlicedTableOffset = 16 + (kExpTableSize + 8 + 64) * (int)sizeof(double);  // + per-lane copies of two constants
-#else
-constexpr int kSlicedTableOffset = 16 + (kExpTableSize + 8) * (int)sizeof(double);
-#endif
+// Shared memory: [mbarrier 16][exp table 128][exp constants 64][per-lane copies of two of them 512][frame geometry 64], then
+// the staged table at a FIXED offset (the screen's records come first, so the hot loop addresses them as
+// constant + the byte offset it reads from the grid), then the swarm arrays.
+constexpr int kSlicedGeomDoubles = 8;  // x_max, y_max, 1/cs, (W/2)/cs, (H/2)/cs (what the fp64 evaluation re-reads every round)
+constexpr int kSlicedTableOffset = 16 + (kExpTableSize + 8 + 64 + kSlicedGeomDoubles) * (int)sizeof(double);
 
 struct SlicedSmem {
   uint64_t* bar;
   double* etab;     // [16]
   double* cst;      // [8] fast_exp constants
-  unsigned char* table;  // records, then grid
+  unsigned char* table;  // fp32 screen records (screened launches), then the grid, then the fp64 records
   Pose* pose;       // [2][P+1]
-  double* partial;  // [2][(P+1)*PW]
+  double* partial;  // [NB][(P+1)*PW], NB = 2 in the cluster form, 1 otherwise (see sliced_swarm_smem_bytes)
   double* wpart;    // [(P+1)*NW] warp partials of the cluster form (unused when CL == 1)
   double* ubuf;     // [2][6P] |Random()| coefficients of the current / next iteration (core.cpp:84)
-  double* cost0;    // [P+1] initial costs
+  double* cost0;    // [P+1] initial costs: aliases the second half of ubuf, which is first written after the barrier that ends the first phase A
   double* x;        // [P][3]  owner-private particle state
   double* v;        // [P][3]
   double* vnew;     // [P][3]
   double* pb;       // [P][3]
   double* pbc;      // [P]
   // fp32 screening (CL == 1 only; null when off)
-  float4* pose32;   // [P+1][2] {x, y, cos, sin}, {-sin, cos, 0, 0} of the current round's candidates (the register pairs the packed transform takes)
+  float4* pose32;   // [P+1][2] {tu, tv, c/cs, s/cs}, {-s/cs, c/cs, 0, 0} of the current round's candidates: the register pairs the packed transform takes
   float* lbpart;    // [(P+1)*NW] per-warp partial sums of the upper bounds
-  int* surv;        // [P+2] candidates that need the fp64 evaluation; surv[P+1] = their number
-  float* rec32;     // [(n_rec+1)][8] {h00, h01, h11, hs, mx, my, -, -}
+  unsigned short* wsurv;  // [NW][P+2] per warp: the candidates that need the fp64 evaluation, ascending
 };
 
-// PW = partials per candidate summed in phase C; WP = warp partials per candidate of the cluster form (0 when CL == 1)
+// PW = partials per candidate summed in phase C; WP = warp partials per candidate of the cluster form (0 when CL == 1).
+// The partials are written by phase B and read by phase C, and a barrier (the one that ends phase A) separates a round's
+// phase C from the next round's phase B, so one buffer suffices; the cluster form fills them through remote stores that a
+// fast CTA may issue while a slow one still reads the previous round's, hence its two buffers.
 __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   const int Pn = P > 0 ? P : 1;
   int b = 2 * (P + 1) * (int)sizeof(Pose);
-  b += 2 * (P + 1) * PW * (int)sizeof(double);
+  b += (WP > 0 ? 2 : 1) * (P + 1) * PW * (int)sizeof(double);
   b += (P + 1) * WP * (int)sizeof(double);
   b += 2 * 6 * Pn * (int)sizeof(double);
-  b += (P + 1) * (int)sizeof(double);
-  b += Pn * 13 * (int)sizeof(double);
+  b += 13 * Pn * (int)sizeof(double);
   return (b + 15) & ~15;
 }
-// shared memory of the fp32 screen without its record table: pose32, lbpart, surv
+// shared memory of the fp32 screen without its record table: pose32, lbpart, wsurv
 __host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
-  return (P + 1) * 32 + round16((P + 1) * NW * 4) + round16((P + 2) * 4);
+  return (P + 1) * 32 + round16((P + 1) * NW * 4) + round16(NW * (P + 2) * 2);
 }
 // total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2).  With the screen (screen_recs > 0:
 // the largest record count of the batch, null record included) the fp32 records take screen_recs * 32 bytes more.
@@ -113,6 +112,8 @@ __host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int tabl
          (screen_recs > 0 ? sliced_screen_fixed_bytes(P, PW) + round16(screen_recs * 32) : 0);
 }
 
+// table_bytes = this CTA's staged table: [fp32 records (screen only)][grid][fp64 records].  Every pointer is `base` plus an
+// integer offset (no pointer/integer round trips), so the compiler keeps them in the shared address space (LDS, not LD).
 __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, int PW, int WP, int table_bytes, int screen = 0) {
   SlicedSmem s;
   const int Pn = P > 0 ? P : 1;
@@ -120,36 +121,32 @@ __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, i
   s.etab = reinterpret_cast<double*>(base + 16);
   s.cst = s.etab + kExpTableSize;
   s.table = base + kSlicedTableOffset;
-  unsigned char* p = s.table + table_bytes;
-  s.pose = reinterpret_cast<Pose*>(p);
-  p += 2 * (P + 1) * sizeof(Pose);
-  s.partial = reinterpret_cast<double*>(p);
-  p += 2 * (size_t)(P + 1) * PW * sizeof(double);
-  s.wpart = reinterpret_cast<double*>(p);
-  p += (size_t)(P + 1) * WP * sizeof(double);
-  s.ubuf = reinterpret_cast<double*>(p);
-  p += 2 * 6 * (size_t)Pn * sizeof(double);
-  s.cost0 = reinterpret_cast<double*>(p);
-  p += (P + 1) * sizeof(double);
-  double* d = reinterpret_cast<double*>(p);
+  int o = kSlicedTableOffset + table_bytes;
+  s.pose = reinterpret_cast<Pose*>(base + o);
+  o += 2 * (P + 1) * (int)sizeof(Pose);
+  s.partial = reinterpret_cast<double*>(base + o);
+  o += (WP > 0 ? 2 : 1) * (P + 1) * PW * (int)sizeof(double);
+  s.wpart = reinterpret_cast<double*>(base + o);
+  o += (P + 1) * WP * (int)sizeof(double);
+  s.ubuf = reinterpret_cast<double*>(base + o);
+  s.cost0 = s.ubuf + 6 * Pn;  // P + 1 <= 6 Pn
+  o += 2 * 6 * Pn * (int)sizeof(double);
+  double* d = reinterpret_cast<double*>(base + o);
   s.x = d;
   s.v = d + 3 * Pn;
   s.vnew = d + 6 * Pn;
   s.pb = d + 9 * Pn;
   s.pbc = d + 12 * Pn;
+  o = kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP);  // rounded to 16
   s.pose32 = nullptr;
   s.lbpart = nullptr;
-  s.surv = nullptr;
-  s.rec32 = nullptr;
+  s.wsurv = nullptr;
   if (screen) {
-    p = base + kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP);
-    s.pose32 = reinterpret_cast<float4*>(p);
-    p += (P + 1) * 32;
-    s.lbpart = reinterpret_cast<float*>(p);
-    p += round16((P + 1) * PW * 4);
-    s.surv = reinterpret_cast<int*>(p);
-    p += round16((P + 2) * 4);
-    s.rec32 = reinterpret_cast<float*>(p);
+    s.pose32 = reinterpret_cast<float4*>(base + o);
+    o += (P + 1) * 32;
+    s.lbpart = reinterpret_cast<float*>(base + o);
+    o += round16((P + 1) * PW * 4);
+    s.wsurv = reinterpret_cast<unsigned short*>(base + o);
   }
   return s;
 }
@@ -162,6 +159,7 @@ struct SliceCtx {
   double x_min, x_max, y_min, y_max, hw, hh, cs, inv_cs, hw_s, hh_s;
   double l2e, ln2hi, ln2lo, c7, c6, c5, c4, c3;  // fast_exp constants kept out of the immediate field
   int gw, base, span, null_id;
+  unsigned goff;  // screened launches: the grid holds goff + 32 * record id (the shared-memory address of the screen's record)
 };
 
 // One scan point against one candidate pose: subtracts exp(-(d' S d)/2) from acc iff the point is
@@ -171,7 +169,7 @@ struct SliceCtx {
 // no validity flag.  The host only selects this kernel for tables whose every Sigma^-1 is finite,
 // symmetric and positive semi-definite (what NDTCell::build produces), so the exponent is <= 0 up
 // to rounding and can never overflow; anything else takes the generic kernel (library exp).
-template <bool FAST_GEOM, int VAR>
+template <bool FAST_GEOM, int VAR, int GSHIFT = 0>
 __device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, double tx, double ty, double c, double s, double& acc) {
   const double x = fma(p.x, c, fma(-p.y, s, tx));  // transform_point, core.h:29-30
   const double y = fma(p.x, s, fma(p.y, c, ty));
@@ -196,7 +194,8 @@ __device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, 
   }
   const unsigned g = static_cast<unsigned>(ix + m.gw * iy - m.base);
   const bool in_strip = inb && (g < static_cast<unsigned>(m.span));
-  const unsigned r = m.grid[in_strip ? g : static_cast<unsigned>(m.span)];
+  const unsigned ge = m.grid[in_strip ? g : static_cast<unsigned>(m.span)];
+  const unsigned r = GSHIFT ? (ge - m.goff) >> GSHIFT : ge;  // screened launches keep goff + id * 32 in the grid
   const double* q = m.rec + 6 * r;
   // the sliced kernel only runs on symmetric tables (S01 == S10 bit for bit, which is what
   // NDTCell::s_calc_covar_inverse produces, ndtcell.cpp:109-110): 40 bytes per record instead of 48
@@ -303,74 +302,137 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 // Results are bit-identical with the screen on or off: a candidate is dropped only when its fp64 cost provably fails the
 // comparison, and survivors are evaluated exactly as before.
 //
-// The bound, per scan point.  Let H = Sigma^-1/2 (positive semi-definite; the host only selects this kernel for such
-// tables), A(d) = d'Hd, so the point's term is -exp(-A(d*)) with d* its exact offset from the cell mean.
-//   * Position.  The fp32 transform is within delta_d of the fp64 one in each coordinate (delta_d from the magnitudes of
-//     the scan, the frame and fp32 rounding; PsoParams::scr_dd2 = delta_d^2).
-//   * Cell.  If the fp32 point lies within beta cell sides of a cell edge (which includes the frame's border: frames are
-//     whole cells), fp32 and fp64 may disagree on the cell: the point counts as the worst case, exp(.) = 1.  Otherwise both
-//     pick the same cell c, and |d_k| <= dmax_k(c), the distance from the mean to the far side of the cell.
-//     A point outside the frame has the term 0 in fp64, so whatever e >= 0 the screen computes for it bounds it: there is no
-//     bounds test (screen_point), and the error terms below, derived for a point inside its cell, need not hold for it.
-//   * Exponent.  With d = d* + eps, |eps_k| <= delta_d, and Cauchy-Schwarz + AM-GM on the cross term,
-//         A(d*) >= (1 - t) A(d) - A(eps)/t,          A(eps) <= hs delta_d^2,   hs = H00 + 2|H01| + H11.
-//     A(d) = z0^2 + z1^2 with z = L'd (Cholesky factor L of H).  In fp32 (factor rounded, two FMAs) each z_k is off by at
-//     most ez_k = 3 * 2^-24 * (sum of |L_kj| dmax_j), and (|z| - ez)^2 >= (1 - t) z^2 - ez^2/t, and the sum of the two
-//     squares carries 2^-22 relative rounding.  Together, with t chosen per record (sqrt of the absolute terms, clamped to
-//     [2^-10, 2^-3]: it balances the relative loosening t A against the absolute one for A of order one):
-//         -A(d*) <= -(1 - t)^2 (1 - 2^-22) Atilde + kappa,     kappa = (ez0^2 + ez1^2)/t + hs delta_d^2 / t
-//     The record stores L scaled by sqrt((1 - t)^2 (1 - 2^-22) log2(e)) and kappa log2(e): the screen evaluates
-//         e = ex2(min(kappa2 - z0~^2 - z1~^2, 0)) >= exp(-A(d*)).
-//     The null record (unbuilt cell, outside the strip) has kappa2 = -1e30: e = 0 without a test.
-//   * ex2.approx (2 ulp), the fp32 product/sums of the accumulation: a 2^-14 slack on the total, and 1e-6 absolute for
-//     results flushed to zero:  L = -(sum (1 + 2^-14)) - 1e-6.
+// Everything is done in CELL units (frames the screen accepts are square, whole cells of a power-of-two side cs, so 1/cs is
+// exact).  Notation: u = 2^-24 (every fp32 operation returns x(1 + eta), |eta| <= u); for a scan point p and a candidate
+// (tx, ty, c, s):   U* = (p_x c - p_y s + tx + W/2)/cs - 1/2   (and V* alike): the point's cell coordinate minus one half
+// as the fp64 evaluation sees it (its own rounding, ~2^-50 relative, is folded into the constants below).
+//
+//   (1) Cell coordinate.  Phase A stores, per candidate, ck = fl(c/cs), sk = fl(s/cs), tu = fl(tx/cs + (W/2)/cs - 1/2)
+//       (computed in fp64, rounded once); the point is held as px~ = fl(p_x), py~ = fl(p_y).  The screen computes
+//           Uf = fl(px~ ck + fl(py~ (-sk) + tu))                                              (two FMAs)
+//       Expanding,  Uf - U* = p_x c/cs [(1+e1)(1+e2)(1+e7) - 1] - p_y s/cs [(1+e3)(1+e4)(1+e6)(1+e7) - 1]
+//                           + tau [(1+e5)(1+e6)(1+e7) - 1],   tau = tx/cs + (W/2)/cs - 1/2,
+//       and |(1+e)^3 - 1| <= 3u + 3u^2 + u^3, |(1+e)^4 - 1| <= 4u + 6u^2 + 4u^3 + u^4 — ALL orders, not only the first:
+//           |Uf - U*| <= (3u + 4u^2)(|p_x|/cs + |tau|) + (4u + 7u^2)|p_y|/cs.
+//       A point that the fp64 evaluation places INSIDE the frame has |tx| <= W/2 + sqrt2 pmax (pmax = largest |coordinate| of
+//       the scan), hence |tau| <= (W + 1.4143 pmax)/cs + 1/2, and the first-order part is u (11.25 pmax + 3 W)/cs + 1.5u.
+//       The host (screen_params, ndtpso_capi.cu) sets
+//           du := 2^-24 (12 pmax' + 3.01 W)/cs + 2^-23,   pmax' = max(pmax, 1)            (PsoParams::scr_du)
+//       whose margin over the first-order part, u (0.75 pmax' + 0.01 W)/cs + 0.5u, exceeds the higher-order terms
+//       (<= 11 u^2 (pmax + W)/cs + 2u^2) and the fp64 side's own rounding (<= 2^-48 (pmax + W)/cs) by orders of magnitude
+//       for every batch the host admits ((pmax + W)/cs <= 2^22).  Hence |Uf - U*| <= du for every in-frame point.
+//       A point OUTSIDE the frame contributes 0 to the fp64 cost, so whatever e >= 0 the screen computes for it bounds its
+//       term: nothing has to hold for it (its index is clamped into the staged strip, so every load is in range).
+//   (2) Cell.  n = fl(Uf + 1.5 2^23) - 1.5 2^23 is Uf rounded to the nearest integer (exact for |Uf| < 2^22), i.e. the
+//       floor of the cell coordinate, and df = Uf - n is exact, |df| <= 1/2.  If |df| <= 1/2 - beta with beta >= du, then
+//       U* lies in the same unit interval: fp32 and fp64 agree on the cell (this also covers the frame's border: frames are
+//       whole cells, so a point within du of the border is within du of a cell edge).  Otherwise the point counts as the
+//       worst case, exp(.) = 1.
+//   (3) Offset from the cell's mean, in cell units.  The record stores o~ = fl(o), o = (mu + W/2)/cs - (n + 1/2) in
+//       [-1/2, 1/2] for a mean inside its cell (any o is handled).  The fp64 evaluation's offset is d* = (U* - n) - o; the
+//       screen's is d~ = fl(df - o~) = d* + eps with
+//           |eps| <= du + u|o| + u(1/2 + |o|)(1 + u) <= delta := du + u(2|o| + 0.51),
+//       and |d*_k| <= dmax_k := max(|-1/2 - o_k|, |1/2 - o_k|) (the point is in the cell), |d~_k| <= dmax_k + delta.
+//   (4) Exponent.  H = (Sigma^-1/2) cs^2 (positive semi-definite: the host only selects this kernel for such tables),
+//       A(d) = d'Hd = |L'd|^2 with H = LL' (Cholesky), so the point's term is -exp(-A(d*)).  For every t in (0, 1) and reals
+//       a, b:  (a - b)^2 >= (1 - t) a^2 - (1/t - 1) b^2   (2ab <= t a^2 + b^2/t); applied to the vectors L'd~ and L'eps,
+//           A(d*) >= (1 - t) A(d~) - (1/t - 1) A(eps),          A(eps) <= hs delta^2,   hs = H00 + 2|H01| + H11.
+//       The screen evaluates z~0 = fl(l~10 d~1 + fl(l~00 d~0)), z~1 = fl(l~11 d~1) with l~ = fl(l sqrt(S)), S below.  Each
+//       product carries at most three roundings, (1 + u)^3 <= 1 + 4u, so |z~_k - sqrt(S) z_k| <= sqrt(S) ez_k with
+//           ez_0 = 4u (l00 (dmax_0 + delta) + |l10| (dmax_1 + delta)),   ez_1 = 4u l11 (dmax_1 + delta),
+//       and again z_k^2 >= (1 - t) z~_k^2/S - (1/t - 1) ez_k^2 (also when |z~_k| < sqrt(S) ez_k: the right side is then <= 0).
+//       xe = fl(-z~1^2 + fl(-z~0^2 + kappa2)) >= kappa2 (1 - 2u') - (z~0^2 + z~1^2)(1 + 2u'), u' = u(1 + u) (the squares
+//       are exact inside the FMAs).  With S = (1 - t)^2 (1 - 2^-22) log2(e) and
+//           kappa2 >= 1.000001 log2(e) [(ez_0^2 + ez_1^2) + hs delta^2]/t        (rounded up)
+//       the chain gives  xe >= -A(d*) log2(e), i.e.  e = ex2(min(xe, 0)) >= exp(-A(d*)).   t is chosen per record: sqrt of
+//       the absolute terms, clamped to [2^-10, 2^-3], which balances the relative loosening t A against the absolute one.
+//       The Cholesky factor is computed in fp64 and shrunk by what its own rounding could add (1e-12 relative on l00, l10;
+//       4e-15 H11 absolute on l11^2 before the root, which also covers cancellation in H11 - l10^2).
+//       The null record (unbuilt cell, outside the strip) has kappa2 = -1e30: e = 0 without a test.
+//   (5) Sum.  ex2.approx is within 2 ulp (2^-22); the per-lane accumulation (NPT multiply-adds with weights 0 or 1), the warp tree (5) and the sum over
+//       the warps (NW - 1) are fp32 additions of non-negative terms: relative error <= (NPT + NW + 4) u < 2^-19 for every
+//       shape launched.  The fp64 evaluation's own deviation from exact arithmetic (FMA roundings in the exponent, ~1e-12
+//       relative in exp; fast_exp 1 ulp; tree sum) is below 2^-36.  Total:  L = -(sum (1 + 2^-14)) - 1e-6, the absolute term
+//       for results flushed to zero (ex2.approx.ftz below 2^-126; the fp64 side flushes too, which only raises its cost).
 // cost >= L because each fp64 term is >= -(upper bound of its exponential).
 struct ScreenCtx {
-  const float* rec32;          // shared: [n_rec + 1][8] = {l00, l11, l10, kappa2, -mx, -my, -, -}
-  const unsigned short* grid;  // shared
-  float2 k2, off2;  // (1/cs, 1/cs) and ((W/2)/cs - 0.5, (H/2)/cs - 0.5): the cell coordinates minus one half
-  float beta_c;     // 0.5 - beta
-  int gw, span;
-  unsigned base;
+  // shared: records [n_rec + 1][32 bytes] = {l00, l11, l10, kappa2, -ox, -oy, -, -} at the 32-bit shared address rec32
+  unsigned rec32;
+  const unsigned short* grid;  // shared: the 32-bit shared ADDRESS of the cell's record (rec32 + 32 * record id; below 2^16)
+  float beta_c;                // 0.5 - beta
+  int gw;
+  unsigned span, nbase;        // nbase = -(first cell of the strip + the magic bits of both coordinates)
 };
+
+// shared-memory loads by 32-bit address: the record's address comes straight out of the grid, no pointer arithmetic
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2_16(unsigned a) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
 
 constexpr float kScreenMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to an integer
 constexpr int kScreenMagicBits = 0x4B400000;     // its bit pattern
 
+// what phase A leaves for the screen: the candidate in cell units, as the register pairs the packed transform takes
+__device__ __forceinline__ void store_pose32(float4* pose32, int j, double x, double y, double c, double s, double inv_cs, double off_u,
+                                             double off_v) {
+  const float ck = static_cast<float>(c * inv_cs), sk = static_cast<float>(s * inv_cs);  // c/cs is exact in fp64: one rounding
+  pose32[2 * j] = make_float4(static_cast<float>(fma(x, inv_cs, off_u)), static_cast<float>(fma(y, inv_cs, off_v)), ck, sk);
+  pose32[2 * j + 1] = make_float4(-sk, ck, 0.f, 0.f);
+}
+
+// This lane's scan points for the screen: the (x, x), (y, y) pairs of the packed transform, and per slot a weight (1 for a
+// scan point, 0 for padding).  A padding slot holds a COPY of one of the lane's own scan points (of the scan's first point in
+// a lane that has none), so it goes through the arithmetic like any point, cannot add a new "near a cell edge" case, and is
+// dropped from the sum by its weight.
+template <int NPT>
+struct ScreenPts {
+  float2 px2[NPT], py2[NPT];
+  float w[NPT];
+};
+
 // One scan point against one candidate, with Blackwell's packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2: two IEEE results per
-// instruction) wherever x and y go through the same operation — the loop is bound by instruction issue, not by the fp32 pipe.
-//   px2 = (px, px), py2 = (py, py);  cs = (cos, sin), sc = (-sin, cos), txy = (tx, ty) of the candidate
-__device__ __forceinline__ void screen_point(const ScreenCtx& m, const float2 px2, const float2 py2, const float2 txy, const float2 cs,
-                                             const float2 sc, float& acc) {
-  const float2 xy = __ffma2_rn(px2, cs, __ffma2_rn(py2, sc, txy));  // transform_point
-  // No bounds test: a point outside the frame contributes 0 to the fp64 cost, so ANY e >= 0 bounds its term.  Outside in y
-  // its index leaves the strip and clamps to the null record; outside in x it aliases to a cell of a neighbouring row, a
-  // frame width away, whose Gaussian is 0 there to fp32 (d is taken from the true position).  Points that fp32 and fp64
-  // place on different sides of the frame's border lie within beta of a cell edge (frames are whole cells): `unc` below.
-  const float2 uv = __ffma2_rn(xy, m.k2, m.off2);                   // cell coordinates - 0.5
-  const float2 t2 = __fadd2_rn(uv, make_float2(kScreenMagic, kScreenMagic));  // round to nearest of (u - 0.5) = floor(u), |u| < 2^22
+// instruction) wherever the two coordinates go through the same operation: the upper bound of the point's exp(.).
+//   px2 = (px, px), py2 = (py, py);  tuv = (tu, tv), cs = (ck, sk), sc = (-sk, ck) of the candidate.
+// 21 instructions; three shared-memory loads (grid entry 2 bytes, record 16 + 8 bytes: 6.6 wavefronts measured), which is what
+// bounds the loop together with instruction issue (profiles/).
+__device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 px2, const float2 py2, const float2 tuv, const float2 cs,
+                                              const float2 sc) {
+  const float2 uv = __ffma2_rn(px2, cs, __ffma2_rn(py2, sc, tuv));             // cell coordinates - 0.5
+  const float2 t2 = __fadd2_rn(uv, make_float2(kScreenMagic, kScreenMagic));   // round to nearest = floor of the cell coordinate, |uv| < 2^22
   const float2 fl = __fadd2_rn(t2, make_float2(-kScreenMagic, -kScreenMagic));
-  const float2 df = __ffma2_rn(fl, make_float2(-1.f, -1.f), uv);    // fractional part - 0.5
-  const bool unc = fmaxf(fabsf(df.x), fabsf(df.y)) > m.beta_c;      // within beta of a cell edge
-  // ix + gw*iy - base with ix = bits(t) - magic bits: the constants are folded into `base`
-  const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y) - m.base;
-  const unsigned gs = min(g, static_cast<unsigned>(m.span));
-  const unsigned r = m.grid[gs];
-  const float* q = m.rec32 + 8 * r;
-  const float4 l = *reinterpret_cast<const float4*>(q);        // l00, l11, l10, kappa2
-  const float2 nmu = *reinterpret_cast<const float2*>(q + 4);  // -mx, -my
-  const float2 d = __fadd2_rn(xy, nmu);
-  const float2 zz = __fmul2_rn(make_float2(l.x, l.y), d);      // l00 d0, l11 d1
+  const float2 df = __fadd2_rn(uv, make_float2(-fl.x, -fl.y));                 // exact: position in the cell - 0.5
+  // ix + gw*iy - (first cell of the strip) with ix = bits(t) - magic bits: the constants are folded into `nbase`;
+  // min(g + nbase, span) is one VIADDMNMX
+  const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y);
+  const unsigned ra = m.grid[__viaddmin_u32(g, m.nbase, m.span)];
+  const float4 l = lds_f4(ra);       // l00, l11, l10, kappa2
+  const float2 no = lds_f2_16(ra);   // -ox, -oy
+  const float2 d = __fadd2_rn(df, no);
+  const float2 zz = __fmul2_rn(make_float2(l.x, l.y), d);                      // l00 d0, l11 d1
   const float z0 = fmaf(l.z, d.y, zz.x);
   const float xe = fmaf(-zz.y, zz.y, fmaf(-z0, z0, l.w));
-  float e;  // ex2.approx: 2 ulp, results below 2^-126 flushed to zero; both covered by the total's slack
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(xe, 0.f)));
-  acc += unc ? 1.0f : e;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(xe, 0.f)));          // 2 ulp, results below 2^-126 flushed: covered by the total's slack
+  return fmaxf(fabsf(df.x), fabsf(df.y)) > m.beta_c ? 1.f : e;                 // within beta of a cell edge: the worst case
 }
 
 // warp sums of JB per-lane accumulators, packed like packed_warp_sum (same slot assignment)
 template <int JB>
 __device__ __forceinline__ float packed_warp_sum_f(const float (&a)[JB], int lane);
+template <>
+__device__ __forceinline__ float packed_warp_sum_f<1>(const float (&a)[1], int) {
+  float k = a[0];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+  return k;
+}
 template <>
 __device__ __forceinline__ float packed_warp_sum_f<2>(const float (&a)[2], int lane) {
   const bool hi16 = (lane & 16) != 0;
@@ -418,33 +480,56 @@ __device__ __forceinline__ float packed_warp_sum_f<8>(const float (&a)[8], int l
 
 // screen of candidates j .. j+JB-1 (clamped to hi-1) on this warp's slice: lbpart[j*NW + warp] = sum of the upper bounds
 template <int NPT, int JB>
-__device__ __forceinline__ void screen_batch(const ScreenCtx& m, const float2 (&px2)[NPT], const float2 (&py2)[NPT], const float4* pose32,
-                                             float* lbpart, int j, int hi, int NW, int warp, int lane) {
+__device__ __forceinline__ void screen_batch(const ScreenCtx& m, const ScreenPts<NPT>& p, const float4* pose32, float* lbpart, int j, int hi,
+                                             int NW, int warp, int lane) {
   float acc[JB];
-  float4 ps[JB];
-  float2 sc2[JB];
 #pragma unroll
   for (int b = 0; b < JB; ++b) {
     const float4* q = pose32 + 2 * min(j + b, hi - 1);
-    ps[b] = q[0];
-    sc2[b] = *reinterpret_cast<const float2*>(q + 1);
-    acc[b] = 0.f;
-  }
+    const float4 ps = q[0];
+    const float2 tuv = make_float2(ps.x, ps.y), cs = make_float2(ps.z, ps.w), sc = *reinterpret_cast<const float2*>(q + 1);
+    acc[b] = screen_point(m, p.px2[0], p.py2[0], tuv, cs, sc) * p.w[0];  // the weight drops padding slots (copies of a scan point)
 #pragma unroll
-  for (int b = 0; b < JB; ++b) {
-    const float2 txy = make_float2(ps[b].x, ps[b].y), cs = make_float2(ps[b].z, ps[b].w), sc = sc2[b];
-#pragma unroll
-    for (int k = 0; k < NPT; ++k) screen_point(m, px2[k], py2[k], txy, cs, sc, acc[b]);
+    for (int k = 1; k < NPT; ++k) acc[b] = fmaf(screen_point(m, p.px2[k], p.py2[k], tuv, cs, sc), p.w[k], acc[b]);
   }
   const float tot = packed_warp_sum_f<JB>(acc, lane);
   const int jj = j + packed_slot<JB>(lane);
   if (packed_writer<JB>(lane) && jj < hi) lbpart[jj * NW + warp] = tot;
 }
 
+// the screen over candidates [lo, hi): NDTPSO_SCREEN_JB at a time, then the rest in pairs
+template <int NPT>
+__device__ __forceinline__ void screen_candidates(const ScreenCtx& m, const ScreenPts<NPT>& p, const float4* pose32, float* lbpart, int lo, int hi,
+                                                  int NW, int warp, int lane) {
+  int j = lo;
+  for (; j + NDTPSO_SCREEN_JB <= hi; j += NDTPSO_SCREEN_JB) screen_batch<NPT, NDTPSO_SCREEN_JB>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+#if NDTPSO_SCREEN_JB > 4
+  for (; j + 4 <= hi; j += 4) screen_batch<NPT, 4>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+#endif
+  for (; j < hi; j += 2) screen_batch<NPT, 2>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+}
+
+// this lane's fp32 copies of its scan points (pt[k] = point k*T + tid of the scan, padding = (1e200, 0)); `first` = the scan's
+// first point, which stands in for the points of a lane that has none
+template <int NPT>
+__device__ __forceinline__ void screen_points(const double2 (&pt)[NPT], const double2 first, ScreenPts<NPT>& p) {
+  const bool none = pt[0].x > 1e199;
+  const double2 own = none ? first : pt[0];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const bool pad = pt[k].x > 1e199;
+    const double2 q = pad ? own : pt[k];
+    const float fx = static_cast<float>(q.x), fy = static_cast<float>(q.y);
+    p.px2[k] = make_float2(fx, fx);
+    p.py2[k] = make_float2(fy, fy);
+    p.w[k] = pad ? 0.f : 1.f;
+  }
+}
+
 // fp64 evaluation of the candidates listed in surv[i .. i+JB-1] (clamped to the last entry)
-template <int NPT, int JB, bool FAST_GEOM, int VAR>
-__device__ __forceinline__ void score_batch_listed(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, const int* surv,
-                                                   int i, int ns, int NW, int warp, int lane) {
+template <int NPT, int JB, bool FAST_GEOM, int VAR, int GSHIFT>
+__device__ __forceinline__ void score_batch_listed(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart,
+                                                   const unsigned short* surv, int i, int ns, int NW, int warp, int lane) {
   double acc[JB];
   double2 txy[JB], cs[JB];
 #pragma unroll
@@ -457,7 +542,7 @@ __device__ __forceinline__ void score_batch_listed(const SliceCtx& m, const doub
 #pragma unroll
   for (int b = 0; b < JB; ++b) {
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b]);
+    for (int k = 0; k < NPT; ++k) slice_point<FAST_GEOM, VAR, GSHIFT>(m, pt[k], txy[b].x, txy[b].y, cs[b].x, cs[b].y, acc[b]);
   }
   const double tot = packed_warp_sum<JB>(acc, lane);
   const int ii = i + packed_slot<JB>(lane);
@@ -575,33 +660,10 @@ __device__ __forceinline__ double candidate_cost(const double* part, int j, int 
   return p0 > 1e299 ? p0 : candidate_total(part, j, PW);
 }
 
-template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
-__device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& sc, const bool scr, const double2 (&pt)[NPT],
-                                            const DevProblem& pr, const PsoParams& prm, const SlicedSmem& sm, const Topo& tp,
-                                            double* __restrict__ out, int* __restrict__ stats) {
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int P = prm.P, I = prm.I, PW = tp.PW;
-  const int* __restrict__ rnd = pr.rnd;
-  NDTPSO_PHASE_DECL
-  Pose* pose0 = sm.pose;
-  Pose* pose1 = sm.pose + (P + 1);
-  // CL == 1: phase C sums the NW warp partials directly (double buffered).
-  // CL > 1 : warps write wpart (single buffer), exchange_partials() fills the double-buffered cpart.
-  double* part0 = sm.partial;
-  double* part1 = sm.partial + (size_t)(P + 1) * PW;
-  double* wpart = sm.wpart;
-  // the 6P velocity coefficients of iteration `iter` -> ubuf[iter & 1]; issued right before a scoring
-  // phase so that the global-memory latency and the conversions hide behind it
-  auto prefetch_draws = [&](int iter) {
-    if (iter >= I) return;
-    double* dst = sm.ubuf + (iter & 1) * 6 * P;
-    const int* src = rnd + 3 + 3 * P + 6 * P * iter;
-    for (int i = tid; i < 6 * P; i += T) dst[i] = fabs(unit_random(src[i]));  // Array2d::Random().abs(), core.cpp:84
-  };
-
-  // ---- initial swarm: task 0 = the seed particle (core.cpp:53,58), task 1+j = particle j (core.cpp:60-61)
-  for (int t = tid; t < P + 1; t += T) {
+// ---- pieces shared by the two bodies ----------------------------------------------------------------
+// initial swarm: task 0 = the seed particle (core.cpp:53,58), task 1+j = particle j (core.cpp:60-61)
+__device__ __forceinline__ void init_candidates(const DevProblem& pr, const int* __restrict__ rnd, int P, Pose* pose0) {
+  for (int t = threadIdx.x; t < P + 1; t += blockDim.x) {
     double pos[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -612,6 +674,90 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
     sincos(pos[2], &s, &c);
     pose0[t] = Pose{pos[0], pos[1], c, s, pos[2], 0.};
   }
+}
+
+// owner-private state of particle j from its initial candidate
+__device__ __forceinline__ void init_particles(const SlicedSmem& sm, int P, const Pose* pose0) {
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    const Pose ps = pose0[1 + j];
+    sm.x[3 * j] = ps.x;
+    sm.x[3 * j + 1] = ps.y;
+    sm.x[3 * j + 2] = ps.th;
+    sm.pb[3 * j] = ps.x;
+    sm.pb[3 * j + 1] = ps.y;
+    sm.pb[3 * j + 2] = ps.th;
+    sm.v[3 * j] = sm.v[3 * j + 1] = sm.v[3 * j + 2] = 0.;
+    sm.pbc[j] = sm.cost0[1 + j];
+  }
+}
+
+// velocity/position update of particle j against gbest (core.cpp:83-90, no contraction); candidate -> pose[j], velocity -> vnew
+__device__ __forceinline__ Pose update_particle(const SlicedSmem& sm, const PsoParams& prm, const double* ucoef, int j, double w, double gb0,
+                                                double gb1, double gb2) {
+  double nx[3], nv[3];
+  const double gb[3] = {gb0, gb1, gb2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double rx = ucoef[6 * j + 2 * k];  // draw 3+3P + 6P*it + 6j + 2k (and +1), prefetched
+    const double ry = ucoef[6 * j + 2 * k + 1];
+    const double xk = sm.x[3 * j + k], vk = sm.v[3 * j + k], pbk = sm.pb[3 * j + k];
+    // core.cpp:85-87: ((w*v) + ((c1*rx)*(pb-x))) + ((c2*ry)*(gb-x)), no contraction
+    const double t1 = __dmul_rn(w, vk);
+    const double t2 = __dmul_rn(__dmul_rn(prm.c1, rx), __dadd_rn(pbk, -xk));
+    const double t3 = __dmul_rn(__dmul_rn(prm.c2, ry), __dadd_rn(gb[k], -xk));
+    nv[k] = __dadd_rn(__dadd_rn(t1, t2), t3);
+    nx[k] = __dadd_rn(xk, nv[k]);  // core.cpp:89
+  }
+  double s, c;
+  sincos(nx[2], &s, &c);
+  sm.vnew[3 * j] = nv[0];
+  sm.vnew[3 * j + 1] = nv[1];
+  sm.vnew[3 * j + 2] = nv[2];
+  return Pose{nx[0], nx[1], c, s, nx[2], 0.};
+}
+
+// particle j takes its candidate (core.cpp:89-96); cj = the candidate's cost, or anything >= pbest when it is known not to improve
+__device__ __forceinline__ void commit_particle(const SlicedSmem& sm, int j, const Pose& ps, double cj) {
+  sm.x[3 * j] = ps.x;
+  sm.x[3 * j + 1] = ps.y;
+  sm.x[3 * j + 2] = ps.th;
+  sm.v[3 * j] = sm.vnew[3 * j];
+  sm.v[3 * j + 1] = sm.vnew[3 * j + 1];
+  sm.v[3 * j + 2] = sm.vnew[3 * j + 2];
+  if (cj < sm.pbc[j]) {
+    sm.pbc[j] = cj;
+    sm.pb[3 * j] = ps.x;
+    sm.pb[3 * j + 1] = ps.y;
+    sm.pb[3 * j + 2] = ps.th;
+  }
+}
+
+// Generic body: one CTA or a cluster per problem, every pending candidate evaluated in fp64.
+template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void sliced_body(const SliceCtx& m, const double2 (&pt)[NPT], const DevProblem& pr, const PsoParams& prm,
+                                            const SlicedSmem& sm, const Topo& tp, double* __restrict__ out, int* __restrict__ stats) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int P = prm.P, I = prm.I, PW = tp.PW;
+  const int* __restrict__ rnd = pr.rnd;
+  NDTPSO_PHASE_DECL
+  Pose* pose0 = sm.pose;
+  Pose* pose1 = sm.pose + (P + 1);
+  // CL == 1: phase C sums the NW warp partials directly (one buffer: see sliced_swarm_smem_bytes).
+  // CL > 1 : warps write wpart (single buffer), exchange_partials() fills the double-buffered cpart.
+  double* part0 = sm.partial;
+  double* part1 = CL == 1 ? sm.partial : sm.partial + (size_t)(P + 1) * PW;
+  double* wpart = sm.wpart;
+  // the 6P velocity coefficients of iteration `iter` -> ubuf[iter & 1]; issued right before a scoring
+  // phase so that the global-memory latency and the conversions hide behind it
+  auto prefetch_draws = [&](int iter) {
+    if (iter >= I) return;
+    double* dst = sm.ubuf + (iter & 1) * 6 * P;
+    const int* src = rnd + 3 + 3 * P + 6 * P * iter;
+    for (int i = tid; i < 6 * P; i += T) dst[i] = fabs(unit_random(src[i]));  // Array2d::Random().abs(), core.cpp:84
+  };
+
+  init_candidates(pr, rnd, P, pose0);
   __syncthreads();
   prefetch_draws(0);
   score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose0, CL == 1 ? part0 : wpart, 0, P + 1, tp, warp, lane);
@@ -632,20 +778,10 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
       gb2 = pose0[1 + j].th;
     }
   }
-  for (int j = tid; j < P; j += T) {  // owner-private state
-    const Pose ps = pose0[1 + j];
-    sm.x[3 * j] = ps.x;
-    sm.x[3 * j + 1] = ps.y;
-    sm.x[3 * j + 2] = ps.th;
-    sm.pb[3 * j] = ps.x;
-    sm.pb[3 * j + 1] = ps.y;
-    sm.pb[3 * j + 2] = ps.th;
-    sm.v[3 * j] = sm.v[3 * j + 1] = sm.v[3 * j + 2] = 0.;
-    sm.pbc[j] = sm.cost0[1 + j];
-  }
+  init_particles(sm, P, pose0);
 
   // ---- iterations
-  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0, n_f64 = P + 1, n_scr = 0;
+  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0, n_f64 = P + 1;
   // Speculation window.  While gbest is improving often (the first iterations: every particle jumps towards gbest),
   // a round speculates only on the next `win` particles, so an improvement discards at most a window's worth of
   // evaluations instead of the rest of the swarm.  An iteration starts with the whole swarm as its window unless the
@@ -661,104 +797,12 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
     // phase A: owners of the pending particles [start, P)
     const int ja = start + ((tid - start) % T + T) % T;  // first pending particle owned by this thread
     const double* ucoef = sm.ubuf + (it & 1) * 6 * P;
-    for (int j = ja; j < lim; j += T) {
-      double nx[3], nv[3];
-      const double gb[3] = {gb0, gb1, gb2};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double rx = ucoef[6 * j + 2 * k];  // draw 3+3P + 6P*it + 6j + 2k (and +1), prefetched
-        const double ry = ucoef[6 * j + 2 * k + 1];
-        const double xk = sm.x[3 * j + k], vk = sm.v[3 * j + k], pbk = sm.pb[3 * j + k];
-        // core.cpp:85-87: ((w*v) + ((c1*rx)*(pb-x))) + ((c2*ry)*(gb-x)), no contraction
-        const double t1 = __dmul_rn(w, vk);
-        const double t2 = __dmul_rn(__dmul_rn(prm.c1, rx), __dadd_rn(pbk, -xk));
-        const double t3 = __dmul_rn(__dmul_rn(prm.c2, ry), __dadd_rn(gb[k], -xk));
-        nv[k] = __dadd_rn(__dadd_rn(t1, t2), t3);
-        nx[k] = __dadd_rn(xk, nv[k]);  // core.cpp:89
-      }
-      double s, c;
-      sincos(nx[2], &s, &c);
-      pose[j] = Pose{nx[0], nx[1], c, s, nx[2], 0.};
-      if (CL == 1 && scr) {
-        const float cf = static_cast<float>(c), sf = static_cast<float>(s);
-        sm.pose32[2 * j] = make_float4(static_cast<float>(nx[0]), static_cast<float>(nx[1]), cf, sf);
-        sm.pose32[2 * j + 1] = make_float4(-sf, cf, 0.f, 0.f);
-      }
-      sm.vnew[3 * j] = nv[0];
-      sm.vnew[3 * j + 1] = nv[1];
-      sm.vnew[3 * j + 2] = nv[2];
-    }
+    for (int j = ja; j < lim; j += T) pose[j] = update_particle(sm, prm, ucoef, j, w, gb0, gb1, gb2);
     __syncthreads();
     NDTPSO_PHASE_MARK(1)
     if (start == 0) prefetch_draws(it + 1);  // first round of an iteration
-    if (CL == 1 && FAST_GEOM && scr) {
-      // phase B1: fp32 lower bound of every pending candidate's cost on this warp's slice
-      float2 px2[NPT], py2[NPT];
-#pragma unroll
-      for (int k = 0; k < NPT; ++k) {  // padding points (1e200, 0) become (1e30, 0): still outside every frame, but finite in fp32
-        const float fx = static_cast<float>(fmin(pt[k].x, 1e30)), fy = static_cast<float>(pt[k].y);
-        px2[k] = make_float2(fx, fx);
-        py2[k] = make_float2(fy, fy);
-      }
-      {
-        int j = start;
-#if NDTPSO_SCREEN_JB8
-        for (; j + 8 <= lim; j += 8) screen_batch<NPT, 8>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
-#endif
-        for (; j + 4 <= lim; j += 4) screen_batch<NPT, 4>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
-        for (; j < lim; j += 2) screen_batch<NPT, 2>(sc, px2, py2, sm.pose32, sm.lbpart, j, lim, tp.NW, warp, lane);
-      }
-      __syncthreads();
-      NDTPSO_PHASE_MARK(5)
-      // warp 0 lists the candidates whose bound does not already rule out an improvement of their particle's best
-      // (core.cpp:94); the others get a cost of +1e300, which phase C treats like any cost that improves nothing
-      if (warp == 0) {
-        int ns = 0;
-        for (int base = start; base < lim; base += 32) {
-          const int j = base + lane;
-          bool alive = false;
-          if (j < lim) {
-            double u = 0.;
-            if ((tp.NW & 3) == 0) {  // rows of 16-byte multiples: vector loads, four independent sums
-              const float4* row = reinterpret_cast<const float4*>(sm.lbpart + j * tp.NW);
-              double u0 = 0., u1 = 0., u2 = 0., u3 = 0.;
-              for (int w2 = 0; w2 < tp.NW / 4; ++w2) {
-                const float4 q = row[w2];
-                u0 += static_cast<double>(q.x);
-                u1 += static_cast<double>(q.y);
-                u2 += static_cast<double>(q.z);
-                u3 += static_cast<double>(q.w);
-              }
-              u = (u0 + u1) + (u2 + u3);
-            } else {
-              for (int w2 = 0; w2 < tp.NW; ++w2) u += static_cast<double>(sm.lbpart[j * tp.NW + w2]);
-            }
-            const double lower = -(u * (1. + 6.103515625e-5)) - 1e-6;  // slack: ex2.approx, fp32 products and sums (2^-14), flushed denormals
-            alive = !(lower >= sm.pbc[j]);
-            if (!alive) part[j * PW] = 1e300;  // candidate_cost() looks at this entry first
-          }
-          const unsigned mask = __ballot_sync(0xffffffffu, alive);
-          if (alive) sm.surv[ns + __popc(mask & ((1u << lane) - 1u))] = j;
-          ns += __popc(mask);
-        }
-        if (lane == 0) sm.surv[P + 1] = ns;
-      }
-      __syncthreads();
-      NDTPSO_PHASE_MARK(6)
-      // phase B2: the fp64 evaluation of the survivors
-      const int ns = sm.surv[P + 1];
-      n_f64 += ns;
-      n_scr += (lim - start) - ns;
-      {
-        int i = 0;
-        for (; i + 4 <= ns; i += 4) score_batch_listed<NPT, 4, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
-        for (; i + 2 <= ns; i += 2) score_batch_listed<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);
-        if (i < ns) score_batch_listed<NPT, 1, FAST_GEOM, VAR>(m, pt, pose, part, sm.surv, i, ns, tp.NW, warp, lane);  // survivors are few: no padding
-      }
-    } else {
-      n_f64 += lim - start;
-      score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, lim, tp, warp, lane);  // phase B
-    }
+    n_f64 += lim - start;
+    score_candidates<NPT, JB, CL, FAST_GEOM, VAR>(m, pt, pose, CL == 1 ? part : wpart, start, lim, tp, warp, lane);  // phase B
     NDTPSO_PHASE_MARK(2)
     if (CL == 1)
       __syncthreads();
@@ -770,7 +814,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
     double cstar = 0.;
     for (int base = start; base < lim && jstar < 0; base += 32) {
       const int j = base + lane;
-      const double cj = (j < lim) ? candidate_cost(part, j, PW) : 0.;
+      const double cj = (j < lim) ? candidate_total(part, j, PW) : 0.;
       const bool imp = (j < lim) && (cj < gbc);
       const unsigned mask = __ballot_sync(0xffffffffu, imp);
       if (mask) {
@@ -780,22 +824,7 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
       }
     }
     const int end = (jstar >= 0) ? jstar + 1 : lim;
-    for (int j = ja; j < end; j += T) {  // commit own particles in [start, end)  (core.cpp:89-96)
-      const Pose ps = pose[j];
-      const double cj = candidate_cost(part, j, PW);
-      sm.x[3 * j] = ps.x;
-      sm.x[3 * j + 1] = ps.y;
-      sm.x[3 * j + 2] = ps.th;
-      sm.v[3 * j] = sm.vnew[3 * j];
-      sm.v[3 * j + 1] = sm.vnew[3 * j + 1];
-      sm.v[3 * j + 2] = sm.vnew[3 * j + 2];
-      if (cj < sm.pbc[j]) {
-        sm.pbc[j] = cj;
-        sm.pb[3 * j] = ps.x;
-        sm.pb[3 * j + 1] = ps.y;
-        sm.pb[3 * j + 2] = ps.th;
-      }
-    }
+    for (int j = ja; j < end; j += T) commit_particle(sm, j, pose[j], candidate_total(part, j, PW));  // own particles in [start, end)
     if (jstar >= 0) {  // core.cpp:102-103
       gbc = cstar;
       gb0 = pose[jstar].x;
@@ -830,10 +859,234 @@ __device__ __forceinline__ void sliced_body(const SliceCtx& m, const ScreenCtx& 
       stats[0] = rounds;
       stats[1] = n_gb;
       stats[2] = n_f64;
-      stats[3] = n_scr;
+      stats[3] = 0;
     }
   }
   if (CL > 1) cluster_barrier();  // no CTA may exit while peers can still store into its shared memory
+}
+
+// the loop-invariant operands of the fp64 point evaluation, re-read from shared memory (see sliced_prologue): the screened
+// body fetches them at the start of every fp64 phase instead of carrying ~30 registers through the screen's loop
+__device__ __forceinline__ void load_slice_ctx(const SlicedSmem& sm, const ScreenCtx& sc, const double* rec, int base, int n_rec, SliceCtx& m) {
+  const volatile double* cst = reinterpret_cast<const volatile double*>(sm.cst);
+  const volatile double* geo = cst + 8 + 64;
+  m.grid = sc.grid;
+  m.rec = rec;
+  m.base = base;
+  m.etab = sm.etab;
+  m.x_max = geo[0];
+  m.y_max = geo[1];
+  m.x_min = -m.x_max;
+  m.y_min = -m.y_max;
+  m.inv_cs = geo[2];
+  m.hw_s = geo[3];
+  m.hh_s = geo[4];
+  m.hw = m.hh = m.cs = 0.;  // the fast geometry does not use them
+  m.l2e = cst[8 + (threadIdx.x & 31)];  // per-lane copies: a lane-dependent address keeps them in vector registers
+  m.c7 = cst[40 + (threadIdx.x & 31)];
+  m.ln2hi = cst[1];
+  m.ln2lo = cst[2];
+  m.c6 = cst[4];
+  m.c5 = cst[5];
+  m.c4 = cst[6];
+  m.c3 = cst[7];
+  m.gw = sc.gw;
+  m.span = static_cast<int>(sc.span);
+  m.null_id = n_rec;
+  m.goff = sc.rec32;
+}
+
+#ifndef NDTPSO_B2_RELOAD
+#define NDTPSO_B2_RELOAD 1  // the fp64 phase re-reads its points (L2) and constants (shared memory) every round instead of holding them in registers through the screen
+#endif
+
+// Screened body (one CTA per problem, fast geometry): every pending candidate is first bounded in fp32 (phase B1); each warp
+// then lists, for itself, the candidates the bound does not rule out and evaluates them in fp64 on its slice (phase B2);
+// phase C looks at the survivors only.  Three barriers per round: after A, after B1, after B2.
+template <int NPT, int VAR>
+__device__ __forceinline__ void sliced_body_screened(const ScreenCtx& sc, const SliceCtx& m0, const double2 (&pt0)[NPT], const DevProblem& pr,
+                                                     const PsoParams& prm, const SlicedSmem& sm, const Topo& tp, int n_rec,
+                                                     double* __restrict__ out, int* __restrict__ stats) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int P = prm.P, I = prm.I, NW = tp.NW;
+  const int* __restrict__ rnd = pr.rnd;
+  NDTPSO_PHASE_DECL
+  Pose* pose0 = sm.pose;
+  Pose* pose1 = sm.pose + (P + 1);
+  double* part = sm.partial;
+  unsigned short* mysurv = sm.wsurv + warp * (P + 2);
+  const double inv_cs = m0.inv_cs, off_u = m0.hw_s - 0.5, off_v = m0.hh_s - 0.5;
+  auto prefetch_draws = [&](int iter) {
+    if (iter >= I) return;
+    double* dst = sm.ubuf + (iter & 1) * 6 * P;
+    const int* src = rnd + 3 + 3 * P + 6 * P * iter;
+    for (int i = tid; i < 6 * P; i += T) dst[i] = fabs(unit_random(src[i]));  // Array2d::Random().abs(), core.cpp:84
+  };
+  // fp64 evaluation of the candidates in mysurv[0 .. ns) on this warp's slice -> part[j*NW + warp]
+  auto score_listed = [&](const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, int ns) {
+    int i = 0;
+    for (; i + 4 <= ns; i += 4) score_batch_listed<NPT, 4, true, VAR, 5>(m, pt, pose, part, mysurv, i, ns, NW, warp, lane);
+    for (; i + 2 <= ns; i += 2) score_batch_listed<NPT, 2, true, VAR, 5>(m, pt, pose, part, mysurv, i, ns, NW, warp, lane);
+    if (i < ns) score_batch_listed<NPT, 1, true, VAR, 5>(m, pt, pose, part, mysurv, i, ns, NW, warp, lane);  // survivors are few: no padding
+  };
+
+  init_candidates(pr, rnd, P, pose0);
+  for (int t = lane; t < P + 1; t += 32) mysurv[t] = static_cast<unsigned short>(t);  // the initial swarm is evaluated in full
+  __syncthreads();
+  prefetch_draws(0);
+  score_listed(m0, pt0, pose0, P + 1);
+  __syncthreads();
+  for (int t = tid; t < P + 1; t += T) sm.cost0[t] = candidate_total(part, t, NW);
+  __syncthreads();
+  // every thread derives the initial gbest the way core.cpp:58-69 does (strict <, index order)
+  double gbc = sm.cost0[0], gb0 = pose0[0].x, gb1 = pose0[0].y, gb2 = pose0[0].th;
+  for (int j = 0; j < P; ++j) {
+    const double cj = sm.cost0[1 + j];
+    if (cj < gbc) {
+      gbc = cj;
+      gb0 = pose0[1 + j].x;
+      gb1 = pose0[1 + j].y;
+      gb2 = pose0[1 + j].th;
+    }
+  }
+  init_particles(sm, P, pose0);
+  ScreenPts<NPT> sp;
+  screen_points<NPT>(pt0, pr.n_pts > 0 ? pr.pts[0] : make_double2(0., 0.), sp);
+
+  int it = 0, start = 0, par = 1, rounds = 0, n_gb = 0, n_f64 = P + 1, n_scr = 0;
+  int hot = prm.hot_chunk > 0 ? 1 : 0, imp_it = 0, win = prm.hot_chunk;  // speculation window: see sliced_body
+  double w = prm.w;
+  NDTPSO_PHASE_MARK(0)
+  while (it < I) {
+    Pose* pose = par ? pose1 : pose0;
+    const int lim = win > 0 ? min(P, start + win) : P;  // this round covers particles [start, lim)
+    // phase A: owners of the pending particles [start, lim)
+    const int ja = start + ((tid - start) % T + T) % T;  // first pending particle owned by this thread
+    const double* ucoef = sm.ubuf + (it & 1) * 6 * P;
+    for (int j = ja; j < lim; j += T) {
+      const Pose ps = update_particle(sm, prm, ucoef, j, w, gb0, gb1, gb2);
+      pose[j] = ps;
+      store_pose32(sm.pose32, j, ps.x, ps.y, ps.c, ps.s, inv_cs, off_u, off_v);
+    }
+    __syncthreads();
+    NDTPSO_PHASE_MARK(1)
+    if (start == 0) prefetch_draws(it + 1);  // first round of an iteration
+    // phase B1: fp32 lower bound of every pending candidate's cost on this warp's slice
+    screen_candidates<NPT>(sc, sp, sm.pose32, sm.lbpart, start, lim, NW, warp, lane);
+#if NDTPSO_B2_RELOAD
+    // the fp64 copies of this thread's points for phase B2: requested now, they arrive while the barrier and the list pass
+    double2 pt[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      const int i = k * T + tid;
+      pt[k] = make_double2(1e200, 0.);  // padding: out of bounds for every pose
+      if (i < pr.n_pts) asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(pt[k].x), "=d"(pt[k].y) : "l"(pr.pts + i));
+    }
+#endif
+    __syncthreads();
+    NDTPSO_PHASE_MARK(5)
+    // every warp lists, for itself, the candidates whose bound does not already rule out an improvement of their particle's
+    // best (core.cpp:94); no barrier needed before phase B2.  The others are marked with a cost of +1e300 in their first
+    // partial (by warp 0), which phase C's commit treats like any cost that improves nothing.
+    int ns = 0;
+    for (int base = start; base < lim; base += 32) {
+      const int j = base + lane;
+      bool alive = false;
+      if (j < lim) {
+        const float* row = sm.lbpart + j * NW;
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+        int w2 = 0;
+        if ((NW & 3) == 0) {  // rows of 16-byte multiples: vector loads
+          for (; w2 < NW; w2 += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(row + w2);
+            u0 += q.x;
+            u1 += q.y;
+            u2 += q.z;
+            u3 += q.w;
+          }
+        }
+        for (; w2 < NW; ++w2) u0 += row[w2];
+        const double u = static_cast<double>((u0 + u1) + (u2 + u3));
+        const double lower = -(u * (1. + 6.103515625e-5)) - 1e-6;  // slack: ex2.approx, fp32 sums (2^-14 in all), flushed denormals
+        alive = !(lower >= sm.pbc[j]);
+        if (!alive && warp == 0) part[j * NW] = 1e300;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, alive);
+      if (alive) mysurv[ns + __popc(mask & ((1u << lane) - 1u))] = static_cast<unsigned short>(j);
+      ns += __popc(mask);
+    }
+    __syncwarp();
+    NDTPSO_PHASE_MARK(6)
+    // phase B2: the fp64 evaluation of the survivors
+    n_f64 += ns;
+    n_scr += (lim - start) - ns;
+    if (ns > 0) {
+#if NDTPSO_B2_RELOAD
+      SliceCtx m;
+      load_slice_ctx(sm, sc, m0.rec, m0.base, n_rec, m);
+      score_listed(m, pt, pose, ns);
+#else
+      score_listed(m0, pt0, pose, ns);
+#endif
+    }
+    NDTPSO_PHASE_MARK(2)
+    __syncthreads();
+    NDTPSO_PHASE_MARK(3)
+    // phase C: j* = first pending particle that improves gbest (core.cpp:98); only survivors can (gbest <= every pbest)
+    int jstar = -1;
+    double cstar = 0.;
+    for (int base = 0; base < ns && jstar < 0; base += 32) {
+      const int i = base + lane;
+      const int j = (i < ns) ? mysurv[i] : 0;
+      const double cj = (i < ns) ? candidate_total(part, j, NW) : 0.;
+      const bool imp = (i < ns) && (cj < gbc);
+      const unsigned mask = __ballot_sync(0xffffffffu, imp);
+      if (mask) {
+        const int src = __ffs(mask) - 1;  // the list is ascending: the first survivor that improves is the first particle that does
+        jstar = __shfl_sync(0xffffffffu, j, src);
+        cstar = __shfl_sync(0xffffffffu, cj, src);
+      }
+    }
+    const int end = (jstar >= 0) ? jstar + 1 : lim;
+    for (int j = ja; j < end; j += T) commit_particle(sm, j, pose[j], candidate_cost(part, j, NW));  // own particles in [start, end)
+    if (jstar >= 0) {  // core.cpp:102-103
+      gbc = cstar;
+      gb0 = pose[jstar].x;
+      gb1 = pose[jstar].y;
+      gb2 = pose[jstar].th;
+      ++n_gb;
+      ++imp_it;
+      win = prm.hot_chunk;
+    } else if (win > 0) {
+      win = min(2 * win, 1 << 20);
+    }
+    start = end;
+    if (start >= P) {
+      start = 0;
+      ++it;
+      w = __dmul_rn(w, prm.wd);  // core.cpp:108
+      hot = (prm.hot_chunk > 0 && imp_it >= prm.hot_thresh) ? 1 : 0;
+      win = hot ? prm.hot_chunk : 0;
+      imp_it = 0;
+    }
+    par ^= 1;
+    ++rounds;
+    NDTPSO_PHASE_MARK(4)
+  }
+
+  if (tid == 0) {
+    out[0] = gb0;
+    out[1] = gb1;
+    out[2] = gb2;
+    out[3] = gbc;
+    if (stats) {
+      stats[0] = rounds;
+      stats[1] = n_gb;
+      stats[2] = n_f64;
+      stats[3] = n_scr;
+    }
+  }
 }
 
 // Prologue shared by the production kernel and the phase-B microbenchmark: stages the compact
@@ -849,19 +1102,21 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   const int span = nrows * mp.gw;
   const int rec_bytes = (n_rec + 1) * 48;
   const int grid_bytes = round16((span + 1) * 2);
-  const SlicedSmem sm = carve_sliced(smem_raw, P, tp.PW, tp.CL == 1 ? 0 : tp.NW, rec_bytes + grid_bytes, screen);
+  const int rec32_bytes = screen ? (n_rec + 1) * 32 : 0;
+  const SlicedSmem sm = carve_sliced(smem_raw, P, tp.PW, tp.CL == 1 ? 0 : tp.NW, rec32_bytes + grid_bytes + rec_bytes, screen);
+  unsigned char* s_rec32 = sm.table;
+  unsigned short* s_grid = reinterpret_cast<unsigned short*>(sm.table + rec32_bytes);
+  unsigned char* s_rec = sm.table + rec32_bytes + grid_bytes;
 
   if (tid < kExpTableSize) sm.etab[tid] = c_exp_table[tid];
   // constants go through volatile shared memory so the compiler keeps them in registers instead of
   // re-materialising 64-bit immediates inside the loop
   volatile double* cst = reinterpret_cast<volatile double*>(sm.cst);
-#if (NDTPSO_PROD_VARIANT & 4)
   if (tid < 32) {
     const ExpConsts ec = exp_consts();
     sm.cst[8 + tid] = ec.l2e;
     sm.cst[40 + tid] = ec.c7;
   }
-#endif
   if (tid == 0) {
     const ExpConsts ec = exp_consts();
     cst[0] = ec.l2e;
@@ -872,14 +1127,20 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
     cst[5] = ec.c5;
     cst[6] = ec.c4;
     cst[7] = ec.c3;
+    volatile double* geo = cst + 8 + 64;  // what load_slice_ctx re-reads
+    geo[0] = mp.x_max;
+    geo[1] = mp.y_max;
+    geo[2] = mp.inv_cs;
+    geo[3] = mp.hw * mp.inv_cs;
+    geo[4] = mp.hh * mp.inv_cs;
     mbar_init(sm.bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(sm.bar, rec_bytes + grid_bytes);
-    tma_load_1d(sm.table, mp.rec, rec_bytes, sm.bar);
-    tma_load_1d(sm.table + rec_bytes, mp.grid, grid_bytes, sm.bar);
+    tma_load_1d(s_rec, mp.rec, rec_bytes, sm.bar);
+    tma_load_1d(s_grid, mp.grid, grid_bytes, sm.bar);
   }
   // slice s of the scan: points k*(S*T) + s*T + tid
 #pragma unroll
@@ -887,8 +1148,8 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
     const int i = (k * tp.S + tp.s) * T + tid;
     pt[k] = (i < pr.n_pts) ? pr.pts[i] : make_double2(1e200, 0.);  // padding: out of bounds for every pose
   }
-  m.rec = reinterpret_cast<const double*>(sm.table);
-  m.grid = reinterpret_cast<const unsigned short*>(sm.table + rec_bytes);
+  m.rec = reinterpret_cast<const double*>(s_rec);
+  m.grid = s_grid;
   m.etab = sm.etab;
   m.x_min = mp.x_min;
   m.x_max = mp.x_max;
@@ -900,20 +1161,13 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   m.inv_cs = mp.inv_cs;
   m.hw_s = mp.hw * mp.inv_cs;
   m.hh_s = mp.hh * mp.inv_cs;
-#if (NDTPSO_PROD_VARIANT & 4)
   {  // per-lane copies: a lane-dependent address is not uniform, so the two constants stay in vector registers
     volatile double* lanes = reinterpret_cast<volatile double*>(sm.cst + 8);
     m.l2e = lanes[tid & 31];
     m.c7 = lanes[32 + (tid & 31)];
   }
-#else
-  m.l2e = cst[0];
-#endif
   m.ln2hi = cst[1];
   m.ln2lo = cst[2];
-#if !(NDTPSO_PROD_VARIANT & 4)
-  m.c7 = cst[3];
-#endif
   m.c6 = cst[4];
   m.c5 = cst[5];
   m.c4 = cst[6];
@@ -922,18 +1176,23 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   m.base = row0 * mp.gw;
   m.span = span;
   m.null_id = n_rec;
+  m.goff = 0u;
   mbar_wait(sm.bar, 0);
   if (screen) {
-    // fp32 records of the screen (see above): one per built cell, found through the grid so that the cell's extent is
-    // known.  Read after the next __syncthreads (the body has one before its first use).
-    const double* rec = reinterpret_cast<const double*>(sm.table);
-    const double dd2 = static_cast<double>(prm->scr_dd2);
-    const double dd = sqrt(dd2);
+    // fp32 records of the screen (derivation above "struct ScreenCtx"): one per built cell, found through the grid so that the
+    // cell is known; the grid entry is then replaced by the record's byte offset.  Every thread owns whole grid entries, and
+    // the body has a __syncthreads before anyone else reads them.
+    const double* rec = reinterpret_cast<const double*>(s_rec);
+    const unsigned rec32_addr = smem_u32(s_rec32);  // sliced_screen_fits() made sure every record's address is below 2^16
+    m.goff = rec32_addr;
+    const double du = static_cast<double>(prm->scr_du);
     const double u24 = 5.9604644775390625e-08;
+    const double cs2 = mp.cs * mp.cs;
     for (int g = tid; g <= span; g += T) {
-      const int r = (g < span) ? m.grid[g] : n_rec;
-      if (g < span && r == n_rec) continue;  // unbuilt cell
-      float* o = sm.rec32 + 8 * r;
+      const int r = (g < span) ? s_grid[g] : n_rec;
+      s_grid[g] = static_cast<unsigned short>(rec32_addr + r * 32);
+      if (g < span && r == n_rec) continue;  // unbuilt cell: points at the null record
+      float* o = reinterpret_cast<float*>(s_rec32 + 32 * r);
       if (r == n_rec) {  // the null record
         o[0] = o[1] = o[2] = 0.f;
         o[3] = -1e30f;
@@ -941,38 +1200,39 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
         continue;
       }
       const double* q = rec + 6 * r;
-      const double mx = q[0], my = q[1], H00 = -q[2], H01 = -q[3], H11 = -q[5];
+      const double H00 = -q[2] * cs2, H01 = -q[3] * cs2, H11 = -q[5] * cs2;  // (Sigma^-1/2) in cell units
       const int cell = g + row0 * mp.gw;
-      const double cx = (cell % mp.gw) * mp.cs - mp.hw, cy = (cell / mp.gw) * mp.cs - mp.hh;  // the cell's low corner
-      const double dm0 = fmax(fabs(cx - mx), fabs(cx + mp.cs - mx)) + dd, dm1 = fmax(fabs(cy - my), fabs(cy + mp.cs - my)) + dd;
-      const double l00 = H00 > 0. ? sqrt(H00) : 0.;
-      const double l10 = l00 > 0. ? H01 / l00 : 0.;
-      const double l11 = sqrt(fmax(H11 - l10 * l10, 0.));
-      // a Cholesky factor that rounding made too large would overstate A: shrink it by what sqrt/div/rounding can add
+      // the mean's offset from the cell's centre, in cell units
+      const double ox = (q[0] + mp.hw) * mp.inv_cs - ((cell % mp.gw) + 0.5), oy = (q[1] + mp.hh) * mp.inv_cs - ((cell / mp.gw) + 0.5);
+      const double dl0 = du + u24 * (2. * fabs(ox) + 0.51), dl1 = du + u24 * (2. * fabs(oy) + 0.51), dl = fmax(dl0, dl1);
+      const double dm0 = fmax(fabs(-0.5 - ox), fabs(0.5 - ox)) + dl0, dm1 = fmax(fabs(-0.5 - oy), fabs(0.5 - oy)) + dl1;
+      // Cholesky factor, shrunk by what its own rounding could add
       const double sh = 1. - 1e-12;
-      const double ez0 = 3. * u24 * (l00 * dm0 + fabs(l10) * dm1), ez1 = 3. * u24 * l11 * dm1;
+      const double l00 = H00 > 0. ? sqrt(H00) * sh : 0.;
+      const double l10 = l00 > 0. ? H01 / l00 * sh : 0.;
+      const double l11 = sqrt(fmax(H11 - l10 * l10 - 4e-15 * H11, 0.)) * sh;
+      const double ez0 = 4. * u24 * (l00 * dm0 + fabs(l10) * dm1), ez1 = 4. * u24 * l11 * dm1;
       const double hs = H00 + 2. * fabs(H01) + H11;
       // t trades the relative loosening t*A against the absolute one kappa0/t: balanced for A of order one
-      const double kappa0 = ez0 * ez0 + ez1 * ez1 + hs * dd2;
+      const double kappa0 = ez0 * ez0 + ez1 * ez1 + hs * dl * dl;
       const double t = fmin(fmax(sqrt(kappa0), 0x1p-10), 0x1p-3);
-      const double scale = sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634);
+      const double scale = sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634) * (1. - 1e-12);
       const double kappa = kappa0 / t * 1.000001;  // and the rounding of the sum it enters
-      o[0] = static_cast<float>(l00 * scale * sh);
-      o[1] = static_cast<float>(l11 * scale * sh);
-      o[2] = static_cast<float>(l10 * scale * sh);
+      // the factor's entries are rounded to fp32 here; that rounding is the first of the three ez counts per product
+      o[0] = static_cast<float>(l00 * scale);
+      o[1] = static_cast<float>(l11 * scale);
+      o[2] = static_cast<float>(l10 * scale);
       o[3] = __double2float_ru(kappa * 1.4426950408889634);
-      o[4] = -static_cast<float>(mx);
-      o[5] = -static_cast<float>(my);
+      o[4] = static_cast<float>(-ox);
+      o[5] = static_cast<float>(-oy);
       o[6] = o[7] = 0.f;
     }
-    sc->rec32 = sm.rec32;
-    sc->grid = m.grid;
-    sc->k2 = make_float2(static_cast<float>(mp.inv_cs), static_cast<float>(mp.inv_cs));
-    sc->off2 = make_float2(static_cast<float>(mp.hw * mp.inv_cs - 0.5), static_cast<float>(mp.hh * mp.inv_cs - 0.5));
+    sc->rec32 = rec32_addr;
+    sc->grid = s_grid;
     sc->beta_c = prm->scr_beta_c;
     sc->gw = mp.gw;
-    sc->base = static_cast<unsigned>(m.base) + static_cast<unsigned>(kScreenMagicBits) * (1u + static_cast<unsigned>(mp.gw));  // folds the magic bits of both coordinates
-    sc->span = m.span;
+    sc->nbase = 0u - (static_cast<unsigned>(m.base) + static_cast<unsigned>(kScreenMagicBits) * (1u + static_cast<unsigned>(mp.gw)));  // folds the magic bits of both coordinates
+    sc->span = static_cast<unsigned>(m.span);
   }
   return sm;
 }
@@ -991,8 +1251,15 @@ __device__ __forceinline__ Topo make_topo(int groups) {
   return tp;
 }
 
+// the screen's records start at a fixed offset of the dynamic shared memory and are addressed by 16-bit shared addresses
+constexpr int kScreenMaxRecords = 1980;  // null record included: 1024 (room for the window's base) + kSlicedTableOffset + 1980 * 32 < 2^16
+__device__ __forceinline__ bool sliced_screen_fits(const unsigned char* smem_raw, int n_rec) {
+  return smem_u32(smem_raw) + kSlicedTableOffset + 32u * static_cast<unsigned>(n_rec + 1) <= 65536u;
+}
+
 // Host guarantees: every table is compact and symmetric and fits the dynamic shared memory;
-// n_pts <= NPT * S * blockDim.x; the grid is n_problems * CL CTAs launched as clusters of CL.
+// n_pts <= NPT * S * blockDim.x; the grid is n_problems * CL CTAs launched as clusters of CL; with prm.screen every table
+// has fewer than kScreenMaxRecords built cells and the fast geometry.
 template <int NPT, int JB, int CL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem* __restrict__ probs, const DevMap* __restrict__ maps,
                                                               PsoParams prm, int groups, double* __restrict__ out, int* __restrict__ stats) {
@@ -1004,15 +1271,18 @@ __global__ void __launch_bounds__(MAXT, MINB) pso_sliced_kernel(const DevProblem
   SliceCtx m;
   ScreenCtx sc;
   double2 pt[NPT];
-  const int screen = (CL == 1) ? prm.screen : 0;  // shared memory is laid out for it whenever the launch asks for it
+  // shared memory is laid out for the screen whenever the launch asks for it; its records must sit below 2^16 in the shared window
+  const int screen = (CL == 1 && mp.fast_geom && sliced_screen_fits(smem_raw, mp.hdr[HDR_NREC])) ? prm.screen : 0;
   const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt, screen, &sc, &prm);
   if (CL > 1) cluster_barrier();  // every CTA's shared memory is carved before anyone stores into it
   double* o = out + 4 * (size_t)b;
   int* s = stats ? stats + kStatsWords * (size_t)b : nullptr;
-  if (mp.fast_geom)
-    sliced_body<NPT, JB, CL, true, kProdVariant>(m, sc, screen != 0, pt, pr, prm, sm, tp, o, s);
+  if (CL == 1 && screen)
+    sliced_body_screened<NPT, kProdVariant>(sc, m, pt, pr, prm, sm, tp, mp.hdr[HDR_NREC], o, s);
+  else if (mp.fast_geom)
+    sliced_body<NPT, JB, CL, true, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
   else
-    sliced_body<NPT, JB, CL, false, kProdVariant>(m, sc, false, pt, pr, prm, sm, tp, o, s);  // the screen's geometry is the fast one
+    sliced_body<NPT, JB, CL, false, kProdVariant>(m, pt, pr, prm, sm, tp, o, s);
   if (threadIdx.x == 0 && tp.rank == 0) publish_result(prm.ex, b, gridDim.x / CL, o);  // the thread that wrote o
 }
 
@@ -1030,35 +1300,27 @@ __global__ void __launch_bounds__(MAXT, 1) screen_bound_kernel(const DevProblem*
   SliceCtx m;
   ScreenCtx sc;
   double2 pt[NPT];
-  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt, 1, &sc, &prm);
   const int tid = threadIdx.x, T = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  if (!mp.fast_geom || !sliced_screen_fits(smem_raw, mp.hdr[HDR_NREC])) {  // no screen for this table: the trivial bound
+    for (int j = tid; j < m_poses; j += T) out[(size_t)b * m_poses + j] = -1e300;
+    return;
+  }
+  const SlicedSmem sm = sliced_prologue<NPT>(smem_raw, pr, mp, prm.P, tp, m, pt, 1, &sc, &prm);
   for (int j = tid; j < m_poses; j += T) {
     const double* p = poses + 3 * ((size_t)b * m_poses + j);
     double s, c;
     sincos(p[2], &s, &c);
-    const float cf = static_cast<float>(c), sf = static_cast<float>(s);
-    sm.pose32[2 * j] = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), cf, sf);
-    sm.pose32[2 * j + 1] = make_float4(-sf, cf, 0.f, 0.f);
+    store_pose32(sm.pose32, j, p[0], p[1], c, s, m.inv_cs, m.hw_s - 0.5, m.hh_s - 0.5);
   }
   __syncthreads();
-  float2 px2[NPT], py2[NPT];
-#pragma unroll
-  for (int k = 0; k < NPT; ++k) {
-    const float fx = static_cast<float>(fmin(pt[k].x, 1e30)), fy = static_cast<float>(pt[k].y);
-    px2[k] = make_float2(fx, fx);
-    py2[k] = make_float2(fy, fy);
-  }
-  {
-    int j = 0;
-    for (; j + 8 <= m_poses; j += 8) screen_batch<NPT, 8>(sc, px2, py2, sm.pose32, sm.lbpart, j, m_poses, tp.NW, warp, lane);
-    for (; j + 4 <= m_poses; j += 4) screen_batch<NPT, 4>(sc, px2, py2, sm.pose32, sm.lbpart, j, m_poses, tp.NW, warp, lane);
-    for (; j < m_poses; j += 2) screen_batch<NPT, 2>(sc, px2, py2, sm.pose32, sm.lbpart, j, m_poses, tp.NW, warp, lane);
-  }
+  ScreenPts<NPT> sp;
+  screen_points<NPT>(pt, pr.n_pts > 0 ? pr.pts[0] : make_double2(0., 0.), sp);
+  screen_candidates<NPT>(sc, sp, sm.pose32, sm.lbpart, 0, m_poses, tp.NW, warp, lane);
   __syncthreads();
   for (int j = tid; j < m_poses; j += T) {
-    double u = 0.;
-    for (int w2 = 0; w2 < tp.NW; ++w2) u += static_cast<double>(sm.lbpart[j * tp.NW + w2]);
-    out[(size_t)b * m_poses + j] = mp.fast_geom ? -(u * (1. + 6.103515625e-5)) - 1e-6 : -1e300;  // the same slack as phase B1
+    float u = 0.f;
+    for (int w2 = 0; w2 < tp.NW; ++w2) u += sm.lbpart[j * tp.NW + w2];
+    out[(size_t)b * m_poses + j] = -(static_cast<double>(u) * (1. + 6.103515625e-5)) - 1e-6;  // the same slack as phase B1
   }
 }
 

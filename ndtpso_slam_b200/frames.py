@@ -37,6 +37,8 @@ def load_library():
     L.ndtpso_frame_build.argtypes = [C.c_void_p]
     L.ndtpso_frame_build.restype = None
     L.ndtpso_frame_is_built.argtypes = [C.c_void_p]
+    L.ndtpso_frame_reset_cells.argtypes = [C.c_void_p]
+    L.ndtpso_frame_reset_cells.restype = None
     L.ndtpso_frame_map_view.argtypes = [C.c_void_p, C.POINTER(capi.MapView)]
     L.ndtpso_frame_map_view.restype = None
     L.ndtpso_frame_sparse_map_view.argtypes = [C.c_void_p, C.POINTER(capi.MapView)]
@@ -60,7 +62,7 @@ def load_library():
 
 #: every symbol include/ndtpso_frames.h declares
 EXPORTS = ["ndtpso_frame_new", "ndtpso_frame_free", "ndtpso_frame_load_laser", "ndtpso_frame_update", "ndtpso_frame_build",
-           "ndtpso_frame_is_built", "ndtpso_frame_map_view", "ndtpso_frame_sparse_map_view", "ndtpso_frame_scan_points",
+           "ndtpso_frame_is_built", "ndtpso_frame_reset_cells", "ndtpso_frame_map_view", "ndtpso_frame_sparse_map_view", "ndtpso_frame_scan_points",
            "ndtpso_frame_point_count", "ndtpso_frame_add_pose", "ndtpso_frame_dump_map", "ndtpso_frame_align", "ndtpso_frame_align_conf", "ndtpso_frame_glir", "ndtpso_frame_cost", "ndtpso_frame_last_cost",
            "ndtpso_frame_last_error"]
 
@@ -96,6 +98,9 @@ class Frame:
 
     def update(self, pose, new_frame: "Frame"):
         self.lib.ndtpso_frame_update(self.h, _d3(pose), new_frame.h)
+
+    def reset_cells(self):
+        self.lib.ndtpso_frame_reset_cells(self.h)
 
     def build(self):
         self.lib.ndtpso_frame_build(self.h)

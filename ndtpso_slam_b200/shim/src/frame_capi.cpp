@@ -50,6 +50,7 @@ void ndtpso_frame_update(ndtpso_frame* f, const double* pose, ndtpso_frame* new_
   f->frame.update(Vector3d(pose[0], pose[1], pose[2]), &new_frame->frame);
 }
 void ndtpso_frame_build(ndtpso_frame* f) { f->frame.build(); }
+void ndtpso_frame_reset_cells(ndtpso_frame* f) { f->frame.resetCells(); }
 int ndtpso_frame_is_built(const ndtpso_frame* f) { return f->frame.built ? 1 : 0; }
 void ndtpso_frame_map_view(const ndtpso_frame* f, ndtpso_map_view* out) { f->frame.mapView(out); }
 void ndtpso_frame_sparse_map_view(const ndtpso_frame* f, ndtpso_map_view* out) { f->frame.sparseMapView(out); }

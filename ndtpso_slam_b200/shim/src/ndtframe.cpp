@@ -165,7 +165,8 @@ void NDTFrame::addPose(double timestamp, const Vector3d& pose, const Vector3d& o
 }
 
 void NDTFrame::resetCells() {
-  for (auto& w : windows_) w->reset();
+  for (auto& w : windows_) w->reset();  // NDTCell::reset (ndtcell.cpp:80-91) leaves `built`, mean and Sigma^-1 as they are
+  scan_cache_valid_ = false;            // the cached scan holds the points that were just dropped
 }
 
 void NDTFrame::dumpMap(const char* filename, bool save_poses, bool save_points, bool /*save_image*/, short /*density*/

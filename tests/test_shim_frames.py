@@ -42,6 +42,21 @@ def test_tables_match_golden_bit_for_bit(golden, name, cfg):
     assert np.array_equal(sp["mean"], want["mean"][b]) and np.array_equal(sp["inv_cov"], want["inv_cov"][b])
 
 
+def test_reset_cells_drops_the_cached_scan():
+    """NDTFrame::resetCells (ndtframe.cpp:208-212) clears every cell's points: a scan read before it must not be served again."""
+    cfg = syn.CFG1
+    ss = syn.scene_a(cfg)
+    s = cfg.sensor
+    f = frames.Frame(width=cfg.map_size_m, height=cfg.map_size_m, cell_side=cfg.map_size_m, calculate_cells_params=False)
+    f.load_laser(ss.query_ranges, s.angle_min, s.angle_increment, s.range_max)
+    assert len(f.scan_points()) > 0
+    f.reset_cells()
+    assert len(f.scan_points()) == 0 and f.point_count() == 0
+    f.load_laser(ss.query_ranges, s.angle_min, s.angle_increment, s.range_max)
+    assert len(f.scan_points()) > 0
+    f.close()
+
+
 def test_trajectory_problem_matches_golden(golden):
     want = golden.flat("traj17")
     got = frames.problem_from_scans(syn.trajectory_problem(syn.CFG2, 17))

@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ndtpso_slam_b200 import capi, workload
-SO = os.path.join(ROOT, "tools", "_build", "libscore_bench.so")
+SO = os.path.join(ROOT, "tools", "_build", os.environ.get("NDTPSO_PHASE_LIB", "libscore_bench.so"))
 capi._build.LIB_PATH = SO  # run the whole C ABI from the instrumented build
 L = capi.load_library()
 L.ndtpso_bench_phase_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]

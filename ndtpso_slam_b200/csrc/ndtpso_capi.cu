@@ -61,7 +61,7 @@ struct ndtpso_ctx {
   int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
   int opt_chunks = 0;      // pipelined align_batch: number of chunks (1 = off, 0 = auto: 3 from 128 problems on)
-  int opt_screen = -1;     // fp32 screening of the sliced kernel: -1 auto (on when the batch qualifies), 0 off, 1 on when it qualifies
+  int opt_screen = -1;     // fp32 screening of the sliced kernel: -1 auto (on when the batch qualifies and it does not cost the second CTA per SM), 0 off, 1 on whenever the batch qualifies
   int opt_hot_chunk = -1;  // speculation window of the sliced kernel while gbest improves often: -1 auto, 0 off
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
@@ -816,7 +816,7 @@ int launch_sliced(ndtpso_batch* bt) {
   const int smem_plain = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, 0));
   int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, scr ? bt->max_n_rec + 1 : 0));
   // not at the price of the second CTA per SM, and not beyond what a CTA may have
-  if (scr && (smem > ctx->max_smem_optin || (smem > ctx->max_smem_optin / 2 && smem_plain <= ctx->max_smem_optin / 2))) {
+  if (scr && (smem > ctx->max_smem_optin || (ctx->opt_screen < 0 && smem > ctx->max_smem_optin / 2 && smem_plain <= ctx->max_smem_optin / 2))) {
     scr = false;
     smem = smem_plain;
   }

@@ -19,6 +19,26 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def batch_golden():
+    from tests.problems import BatchGolden
+    return BatchGolden()
+
+
+@pytest.fixture(scope="session")
+def traj_batch():
+    """The trajectory problems of configs[2] / configs[3], built on demand and kept for the session: traj_batch(n) -> first n."""
+    from ndtpso_slam_b200 import workload
+    cache = []
+
+    def get(n):
+        if len(cache) < n:
+            cache.extend(workload.cfg2_batch(n - len(cache), first=len(cache)))
+        return cache[:n]
+
+    return get
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle.binding import Oracle
     return Oracle()

@@ -69,6 +69,49 @@ SOLVED = [("cfg1", "cfg1"), ("cfg2", "cfg2"), ("align_default", "align_default")
           ("edge_empty_scan", "edge"), ("np2", "np2")]
 
 
+BATCH_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batch_vectors.npz")
+
+
+class BatchGolden:
+    """tests/golden/batch_vectors.npz (make_golden_batch.py): the unmodified reference's pose and cost for every trajectory problem
+    of BASELINE.json configs[2] (b < 256) and configs[3] (b < 2048), and four more seeds of every configs[4] case."""
+
+    def __init__(self, path=BATCH_GOLDEN):
+        z = np.load(path)
+        self.pose, self.cost, self.table_crc = z["traj/pose"], z["traj/cost"], z["traj/table_crc"]
+        self.P, self.I = (int(v) for v in z["traj/pso"])
+        self.z = z
+
+    def cfg5_more(self, cs):
+        """(seeds, pose[n, 3], cost[n]) of the extra seeds of the configs[4] case with cell side `cs`."""
+        k = f"cfg5_{cs}_more"
+        return [int(s) for s in self.z[k + "/seeds"]], self.z[k + "/pose"], self.z[k + "/cost"]
+
+
+def table_crc(flat) -> int:
+    """CRC-32 of a dense flat problem's table and scan, as make_golden_batch.py takes it of the reference's own arrays."""
+    import zlib
+    c = 0
+    for k in ("mean", "inv_cov", "built", "points"):
+        c = zlib.crc32(np.ascontiguousarray(flat[k]).tobytes(), c)
+    return c
+
+
+def oracle_pso_many(oracle, flats, P, I, workers=None):
+    """The oracle on every problem of `flats` (its own seed each), on `workers` threads (the C restatement is re-entrant and
+    ctypes releases the GIL).  Returns pose[n, 3], cost[n]."""
+    from concurrent.futures import ThreadPoolExecutor
+    workers = workers or os.cpu_count() or 1
+
+    def one(f):
+        po, co, _ = oracle.pso(f, f["guess"], f["deviation"], P, I, seed=f["seed"])
+        return po, co
+
+    with ThreadPoolExecutor(workers) as ex:
+        res = list(ex.map(one, flats))
+    return np.array([r[0] for r in res]), np.array([r[1] for r in res])
+
+
 def empty_points(flat):
     f = dict(flat)
     f["points"] = np.zeros((0, 2))

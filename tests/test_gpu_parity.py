@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from ndtpso_slam_b200 import capi
-from tests.problems import POSE_ATOL, SCORE_RTOL, SOLVED, empty_points, rel_err
+from tests.problems import POSE_ATOL, SCORE_RTOL, SOLVED, empty_points, oracle_pso_many, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -259,18 +259,26 @@ def test_indefinite_inverse_covariance(oracle, ctx):
     assert np.abs(pose[0] - po).max() <= POSE_ATOL and rel_err(cost[0], co) <= SCORE_RTOL
 
 
-def test_cfg3_batch_against_oracle(oracle, ctx):
-    """BASELINE.json configs[2]: a batch of 256 trajectory problems (own table each), 70 x 50.
-    Every result is finite and near the true pose; a sample of them is checked against the oracle."""
-    from ndtpso_slam_b200 import synthetic as syn, workload
-    flats = workload.cfg2_batch(256)
+def _parity(pose, cost, want_pose, want_cost, what):
+    dp = np.abs(pose - want_pose).max(axis=1)
+    ds = rel_err(cost, want_cost)
+    assert dp.max() <= POSE_ATOL, (what, int(dp.argmax()), dp.max())
+    assert ds.max() <= SCORE_RTOL, (what, int(ds.argmax()), ds.max())
+    return int((dp == 0).sum())
+
+
+def test_cfg3_batch_against_reference_and_oracle(oracle, ctx, batch_golden, traj_batch):
+    """BASELINE.json configs[2]: a batch of 256 trajectory problems (own table each), 70 x 50.  EVERY result is compared with
+    the unmodified reference's (golden vectors) and with the oracle run here on the same inputs."""
+    from ndtpso_slam_b200 import synthetic as syn
+    flats = traj_batch(256)
     cf = capi.PsoConfig.make(population=70, iterations=50)
     pose, cost = ctx.align_batch(flats, cf)
-    assert np.isfinite(pose).all() and (cost < -300).all()
-    for b in (0, 1, 37, 128, 255):
-        po, co, _ = oracle.pso(flats[b], flats[b]["guess"], flats[b]["deviation"], 70, 50, seed=flats[b]["seed"])
-        assert np.abs(pose[b] - po).max() <= POSE_ATOL, b
-        assert rel_err(cost[b], co) <= SCORE_RTOL, b
+    exact = _parity(pose, cost, batch_golden.pose[:256], batch_golden.cost[:256], "vs reference")
+    assert exact >= 250, exact  # the swarm arithmetic is uncontracted: poses are bit-identical unless a comparison flips
+    po, co = oracle_pso_many(oracle, flats, 70, 50)
+    _parity(pose, cost, po, co, "vs oracle")
+    assert np.array_equal(po, batch_golden.pose[:256])  # and the oracle itself is the reference, bit for bit, on all of them
     # idempotence / determinism at full size: the same batch again, and as two halves
     pose2, cost2 = ctx.align_batch(flats, cf)
     assert np.array_equal(pose, pose2) and np.array_equal(cost, cost2)
@@ -280,6 +288,38 @@ def test_cfg3_batch_against_oracle(oracle, ctx):
     truth = np.array([syn.trajectory_problem(syn.CFG2, b).true_pose for b in range(256)])
     err = np.abs(pose - truth)
     assert np.median(err[:, :2].max(axis=1)) < 0.02 and np.median(err[:, 2]) < 0.004
+
+
+def test_cfg4_every_shard_against_reference(ctx, batch_golden, traj_batch):
+    """BASELINE.json configs[3]: 2048 trajectory problems in shards of 256 (what each of 8 GPUs gets).  Every shard is solved
+    here on one GPU and every one of the 2048 results is compared with the unmodified reference's golden vectors."""
+    flats = traj_batch(2048)
+    cf = capi.PsoConfig.make(population=70, iterations=50)
+    exact = 0
+    for r in range(8):
+        pose, cost = ctx.align_batch(flats[256 * r:256 * (r + 1)], cf)
+        exact += _parity(pose, cost, batch_golden.pose[256 * r:256 * (r + 1)], batch_golden.cost[256 * r:256 * (r + 1)], f"shard {r}")
+    assert exact >= 2000, exact
+    # one launch of all 2048 gives the same answers as the shards (a problem's result does not depend on its batch)
+    pose, cost = ctx.align_batch(flats, cf)
+    _parity(pose, cost, batch_golden.pose, batch_golden.cost, "one batch of 2048")
+
+
+@pytest.mark.parametrize("cs", [0.25, 0.5, 1.0, 2.0])
+def test_cfg5_more_seeds(golden, ctx, batch_golden, cs):
+    """BASELINE.json configs[4] (200 x 100 on four cell sizes): four more seeds per cell size against the unmodified reference."""
+    c = golden.case(f"cfg5_{cs}")
+    base = golden.flat(f"cfg5_{cs}")
+    seeds, want_pose, want_cost = batch_golden.cfg5_more(cs)
+    flats = []
+    for s in seeds:
+        f = dict(base)
+        f.update(guess=c["guess"], deviation=c["deviation"], seed=s)
+        flats.append(f)
+    for n_copies in (1, 40):  # a small batch (cluster form) and one that takes the one-CTA-per-problem, screened form
+        pose, cost = ctx.align_batch(flats * n_copies, conf_of(c))
+        for k in range(n_copies):
+            _parity(pose[k * len(seeds):(k + 1) * len(seeds)], cost[k * len(seeds):(k + 1) * len(seeds)], want_pose, want_cost, (cs, n_copies))
 
 
 @pytest.mark.parametrize("case,inputs", [("cfg1", "cfg1"), ("cfg2", "cfg2"), ("traj17", "traj17"), ("cfg5_0.25", "cfg5_0.25"), ("cfg5_2.0", "cfg5_2.0"),

@@ -1,0 +1,131 @@
+"""Soak of the fp32 screen (ndtpso_pso_sliced.cuh): its lower bound must never exceed the fp64 cost, and switching it on must
+never change a result.  More than 10^6 poses and 10^4 PSO problems on random tables: cell sides 0.25 .. 2 m, frames of 20, 50
+and 100 m, inverse covariances from broad to needle-sharp and correlated up to 0.9999, means anywhere in their cells (corners
+included), ranges up to 30 m, points on cell edges, on the frame's border and outside it, headings far beyond 2 pi, poses from
+converged to hundreds of metres away.
+"""
+import numpy as np
+import pytest
+
+from ndtpso_slam_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = [(20.0, 0.25), (20.0, 0.5), (20.0, 1.0), (20.0, 2.0), (50.0, 0.25), (50.0, 0.5), (50.0, 1.0), (50.0, 2.0),
+         (100.0, 0.5), (100.0, 1.0), (100.0, 2.0), (100.0, 0.25)]
+
+
+def random_problem(rng, width, cs, n_pts):
+    """One random table + scan.  Built cells lie in a band of rows so that the staged row strip fits shared memory."""
+    gw = int(round(width / cs))
+    n = gw * gw
+    band = min(gw, max(4, int(30000 / (2 * gw))))           # rows of the strip: <= ~30 KB of u16 entries
+    row0 = int(rng.integers(0, gw - band + 1))
+    rows = np.arange(n) // gw
+    inside = (rows >= row0) & (rows < row0 + band)
+    built = (inside & (rng.random(n) < min(0.3, 900.0 / max(inside.sum(), 1)))).astype(np.uint8)
+    ix, iy = np.arange(n) % gw, np.arange(n) // gw
+    frac = rng.random((n, 2))
+    corner = rng.random(n) < 0.05                            # some means exactly on a corner / edge of their cell
+    frac[corner] = np.round(frac[corner])
+    mean = np.stack([(ix + frac[:, 0]) * cs - width / 2, (iy + frac[:, 1]) * cs - width / 2], 1)
+    scale = 10.0 ** rng.uniform(-1.0, 6.5, n)                # Sigma^-1 from 0.1 to 3e6 per m^2
+    a, b = scale * rng.uniform(0.2, 1.0, n), scale * rng.uniform(0.2, 1.0, n)
+    r = rng.choice([0.0, 0.5, 0.99, 0.9999], n) * rng.choice([-1.0, 1.0], n) * np.sqrt(a * b)
+    icov = np.stack([a, r, r, b], 1)
+    idx_b = np.nonzero(built)[0]
+    # the sensor's true pose: inside the built band; the scan is what it would see of the map (a point near the mean of a
+    # built cell within 30 m, spread like the cell's Gaussian) plus clutter: points anywhere up to 30 m away, points snapped
+    # to cell edges, points a hair inside / outside the frame's border
+    true = np.array([rng.uniform(-0.2, 0.2) * width, (row0 + band / 2) * cs - width / 2, rng.uniform(-3.0, 3.0)])
+    near = idx_b[np.hypot(mean[idx_b, 0] - true[0], mean[idx_b, 1] - true[1]) < 30.0]
+    pick = rng.choice(near if len(near) else idx_b, n_pts)
+    world = mean[pick] + rng.normal(size=(n_pts, 2)) / np.sqrt(np.stack([a[pick], b[pick]], 1))
+    k = n_pts // 8
+    rad, ang = rng.uniform(0.1, 30.0, k), rng.uniform(-np.pi, np.pi, k)
+    world[:k] = true[:2] + np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1)
+    world[k:2 * k] = np.round(world[k:2 * k] / cs) * cs
+    world[2 * k:2 * k + 10, 0] = width / 2 - 1e-9 * rng.random(10)
+    world[2 * k + 10:2 * k + 20, 1] = -width / 2 + 1e-9 * rng.random(10)
+    world[2 * k + 20:2 * k + 30, 0] = width / 2 + 1e-9 * rng.random(10)
+    c0, s0 = np.cos(true[2]), np.sin(true[2])
+    dxy = world - true[:2]
+    pts = np.stack([c0 * dxy[:, 0] + s0 * dxy[:, 1], -s0 * dxy[:, 0] + c0 * dxy[:, 1]], 1)  # R(-theta)(world - t)
+    centre = true
+    idx = np.nonzero(built)[0].astype(np.int32)  # the sparse form of the ABI: the host need not scan 160 000-cell tables per call
+    flat = dict(points=pts, mean=np.ascontiguousarray(mean[idx]), inv_cov=np.ascontiguousarray(icov[idx]), cell_index=idx, w_cells=gw, h_cells=gw,
+                width_m=width, height_m=width, cell_side=cs, x_min=-width / 2, x_max=width / 2, y_min=-width / 2, y_max=width / 2)
+    return flat, centre
+
+
+def pose_sets(rng, centre, width, m):
+    """m poses: a quarter each converged / spread / diverged-and-spun / far away."""
+    q = m // 4
+    base = np.asarray(centre, dtype=np.float64)
+    conv = base + rng.normal(size=(q, 3)) * np.array([0.003, 0.003, 0.0005])
+    spread = base + rng.normal(size=(q, 3)) * np.array([0.3, 0.3, 0.05])
+    spun = base + rng.normal(size=(q, 3)) * np.array([width / 4, width / 4, 1.0])
+    spun[:, 2] += rng.choice([0.0, 2 * np.pi * 7, -2 * np.pi * 1000, 12345.678], q)     # |theta| >> 2 pi
+    far = base + rng.uniform(-1, 1, size=(m - 3 * q, 3)) * np.array([4 * width, 4 * width, 50.0])
+    far[::7, :2] = rng.uniform(-1, 1, size=(len(far[::7]), 2)) * 1e5                      # hundreds of km away
+    return np.concatenate([conv, spread, spun, far])
+
+
+def test_bound_never_exceeds_cost_one_million_poses(ctx):
+    rng = np.random.default_rng(2026)
+    n_checked, n_tight, worst = 0, 0, 0.0
+    for rep in range(3):
+        flats, centres = [], []
+        for (width, cs) in GEOMS * 2:
+            f, c = random_problem(rng, width, cs, int(rng.integers(300, 1200)))
+            flats.append(f)
+            centres.append(c)
+        for call in range(14):
+            poses = np.stack([pose_sets(rng, c, f["width_m"], 1024) for f, c in zip(flats, centres)])
+            try:
+                lower = ctx.screen_bounds(flats, poses)
+            except capi.NdtpsoError as e:  # a batch the screen refuses is not a failure of the bound
+                assert e.code == capi.ERR_LIMIT, e
+                continue
+            cost = ctx.cost_batch(flats, poses)
+            bad = lower > cost
+            assert not bad.any(), (rep, call, np.argwhere(bad)[:3], lower[bad][:3], cost[bad][:3])
+            n_checked += lower.size
+            hit = cost < -1.0
+            n_tight += int((hit & (lower > 1.2 * cost - 1e-3)).sum())
+            worst = max(worst, float((cost - lower)[hit].max()) if hit.any() else 0.0)
+    assert n_checked >= 1_000_000, n_checked
+    assert n_tight > 1000, n_tight  # the bound is not vacuous: many poses with a real score are bounded within 20 %
+
+
+def test_screen_on_equals_off_ten_thousand_problems():
+    rng = np.random.default_rng(77)
+    conf = capi.PsoConfig.make(population=24, iterations=10)
+    total, settled, evals = 0, 0, 0
+    for rep in range(6):
+        flats = []
+        for (width, cs) in GEOMS:
+            f, c = random_problem(rng, width, cs, int(rng.integers(300, 1200)))
+            for s in range(144):
+                g = dict(f)
+                wide = s % 3 == 0
+                g.update(guess=(c[0] + rng.normal() * 0.05, c[1] + rng.normal() * 0.05, c[2] + rng.normal() * 0.01 + (2 * np.pi * 50 if s % 11 == 0 else 0.0)),
+                         deviation=(2.0, 2.0, 0.8) if wide else (0.1, 0.1, 0.01), seed=int(rng.integers(1, 2 ** 31)))
+                flats.append(g)
+        out = {}
+        for scr in (0, 1):
+            cx = capi.Context(0)
+            cx.set_option(capi.OPT_SCREEN, scr)
+            cx.set_option(capi.OPT_CLUSTER, 1)
+            bt = cx.batch(flats, conf)
+            bt.solve()
+            out[scr] = bt.results() + (bt.stats_ex(),)
+            bt.close()
+            cx.close()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), rep
+        assert np.array_equal(out[0][2][:, :2], out[1][2][:, :2])
+        total += len(flats)
+        settled += int(out[1][2][:, 3].sum())
+        evals += int(out[1][2][:, 2].sum() + out[1][2][:, 3].sum())
+    assert total >= 10_000, total
+    assert settled > 0.3 * evals, (settled, evals)  # the screen did take part

@@ -71,3 +71,32 @@ def test_align_chain(golden, oracle):
         assert rc == 0
         assert np.array_equal(pose, want[k]), (k, pose, want[k])
         guess = pose.copy()
+
+
+def test_batch_golden_inputs_and_oracle(oracle, batch_golden, traj_batch):
+    """tests/golden/batch_vectors.npz: the drop-in NDTFrame rebuilds the reference's tables and scans of the trajectory problems
+    bit for bit (CRC of the reference's own arrays), and the oracle reproduces the reference's results on a sample of them."""
+    from tests.problems import oracle_pso_many, table_crc
+    flats = traj_batch(256)
+    for b, f in enumerate(flats):
+        assert table_crc(f) == int(batch_golden.table_crc[b]), b
+    sample = [0, 1, 37, 100, 128, 200, 255]
+    po, co = oracle_pso_many(oracle, [flats[b] for b in sample], batch_golden.P, batch_golden.I)
+    assert np.array_equal(po, batch_golden.pose[sample])
+    assert np.array_equal(co, batch_golden.cost[sample])
+
+
+@pytest.mark.parametrize("cs", [0.25, 0.5, 1.0, 2.0])
+def test_cfg5_more_seeds_bit_exact(golden, oracle, batch_golden, cs):
+    """configs[4] (200 x 100): the oracle against the unmodified reference on four more seeds per cell size."""
+    from tests.problems import oracle_pso_many
+    c = golden.case(f"cfg5_{cs}")
+    base = golden.flat(f"cfg5_{cs}")
+    seeds, want_pose, want_cost = batch_golden.cfg5_more(cs)
+    flats = []
+    for s in seeds:
+        f = dict(base)
+        f.update(guess=c["guess"], deviation=c["deviation"], seed=s)
+        flats.append(f)
+    po, co = oracle_pso_many(oracle, flats, c["P"], c["I"])
+    assert np.array_equal(po, want_pose) and np.array_equal(co, want_cost)

@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py — scan-matches/sec of the PSO/NDT hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload cfg2|cfg5] [--impl b200|reference]
 
-A step = one pass of the hot path (pso_optimization, 70 particles x 50 iterations, 1081-beam scan
-vs 50 m / 0.5 m NDT map) over a batch of B independent scan-match problems per GPU, each carrying
-its own dense (mu, Sigma^-1, built) table.
+A step = one pass of the hot path (pso_optimization: the whole swarm run) over a batch of B independent scan-match problems per
+GPU, each carrying its own dense (mu, Sigma^-1, built) table.  Workloads:
+  cfg2 (default)  BASELINE.json configs[1] shape batched as configs[2] / configs[3]: 1081-beam scans vs 50 m / 0.5 m NDT maps,
+                  70 particles x 50 iterations; problem b of rank r is step r*B + b of the replayed trajectory
+  cfg5            BASELINE.json configs[4]: the multi-resolution sweep, cell sides 0.25 / 0.5 / 1 / 2 m, 200 particles x 100
+                  iterations; the items (cell side, frame) go round-robin over the ranks by frame, so every GPU holds B/4
+                  frames of every cell side (B = 148 by default)
 
   value      whole-job matches/s with the batch resident in HBM (dense tables, points, guesses): every step runs
-             K0 table compaction + K1 rand() stream + K2 PSO (+ the result exchange for N > 1); two resident copies
-             of the batch alternate on two streams so that consecutive steps overlap; CUDA events around the K steps
+             K0 table compaction + K1 rand() stream + K2 PSO (+ the result exchange for N > 1); four resident copies
+             of the batch are cycled on two streams so that consecutive steps overlap; CUDA events around the K steps
+  sustained  the same loop kept running for at least 2 s (clocks sampled meanwhile)
   single_stream  the same with one copy on one stream, L2 flushed between steps (per-step events)
   e2e        the same metric through ndtpso_align_submit/collect with HOST buffers (pinned): H2D of every
              input + kernels + D2H of the poses inside the timed region, three batches in flight (--e2e-depth)
-  tracking   the reference's whole per-scan callback (loadLaser -> align -> update) on device-resident maps
-  roofline   dominant kernel (pso_sliced_kernel): algorithmic bytes / its duration vs the measured HBM peak;
-             the fp64 pipe fraction beside it (the bound that really binds)
-  cpu_baseline  the reference's own CPU path (oracle/_ref if present, else the oracle port) on
-             this box's host cores, bounded sample
+  parity     every result of the timed batch against the unmodified reference: golden vectors for all of them (every rank),
+             and the reference itself run in this bench on the batch's own first problems (the cpu_baseline leg)
+  tracking   the reference's whole per-scan callback (loadLaser -> align -> update) on device-resident maps (cfg2)
+  roofline   dominant kernel (pso_sliced_kernel): algorithmic bytes / its duration vs the measured HBM peak; beside it the fp64
+             pipe fraction and the shared-memory data pipe, which is the resource that binds (ncu, profiles/)
+  cpu_baseline  the reference's own CPU path (oracle/_ref if present, else the oracle port) on this box's host cores, on the
+             batch's own first problems
 
 `--impl reference` times only the CPU arm, same metric/config.
 """
@@ -36,25 +43,83 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "scan-matches/sec (1081-pt scan, 70 particles x 50 iters)"
-P, I = 70, 50
-ALG_BYTES_PER_MATCH = 16 * 1081 + 49 * 10000 + 80          # 507 376 B
-ALG_FLOP_PER_MATCH = 31 * (P + 1 + P * I) * 1081 + 17 * P * I  # ~119.7 MFLOP
+POSE_ATOL, SCORE_RTOL = 1e-4, 1e-5  # BASELINE.json north_star: parity bar of the path
+CFG5_SIZES = (0.25, 0.5, 1.0, 2.0)
 
 
 # ------------------------------------------------------------------------------------------
-# workload
+# workloads
 # ------------------------------------------------------------------------------------------
-def make_problems(batch, rank):
-    """`batch` cfg2-shaped problems for this rank, every one with its own table arrays."""
-    from ndtpso_slam_b200 import workload
-    return workload.cfg2_batch(batch, first=rank * batch)
+class Workload:
+    """What a rank solves per step, and where the reference's answers for it come from."""
+
+    def __init__(self, name, batch):
+        self.name, self.B = name, batch
+        if name == "cfg2":
+            self.P, self.I = 70, 50
+            self.metric = "scan-matches/sec (1081-pt scan, 70 particles x 50 iters)"
+        else:
+            self.P, self.I = 200, 100
+            self.metric = "scan-matches/sec (1081-pt scan, 200 particles x 100 iters, multi-resolution sweep 0.25/0.5/1/2 m)"
+            if batch % 4:
+                raise SystemExit("bench.py: --batch must be a multiple of 4 for the cfg5 workload (four cell sides per frame)")
+
+    def specs(self, rank, world):
+        """One (cell side, frame index) per problem of this rank; the frame index is also what seeds the problem (1 + frame)."""
+        if self.name == "cfg2":
+            return [(0.5, rank * self.B + b) for b in range(self.B)]
+        # cfg5: item (c, f) -> rank f % world; a rank's batch is frame-major so that the four cell sides alternate
+        return [(cs, rank + world * k) for k in range(self.B // 4) for cs in CFG5_SIZES]
+
+    def problems(self, rank, world, sparse=False):
+        return [make_problem(self.name, cs, f, sparse) for cs, f in self.specs(rank, world)]
+
+    def alg_bytes(self):
+        """16 N + 49 C + 80 bytes per match (mean over the batch for the sweep)."""
+        cells = [int(round(50.0 / cs)) ** 2 for cs in ((0.5,) if self.name == "cfg2" else CFG5_SIZES)]
+        return float(np.mean([16 * 1081 + 49 * c + 80 for c in cells]))
+
+    def alg_flop(self):
+        return 31 * (self.P + 1 + self.P * self.I) * 1081 + 17 * self.P * self.I
+
+    def describe(self):
+        if self.name == "cfg2":
+            return (f"cfg2 shape (configs[1]; batched as configs[2]): {self.B} independent 1081-beam scan-matches per GPU vs "
+                    "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations")
+        return (f"cfg5 (configs[4]): multi-resolution sweep, {self.B} scan-matches per GPU = {self.B // 4} frames x cell sides "
+                "0.25/0.5/1/2 m of a 50 m map (one dense table per problem), 200 particles x 100 iterations, items round-robin over the ranks by frame")
+
+    def golden(self, rank, world):
+        """(pose[B, 3], cost[B]) of the unmodified reference for this rank's problems, or None where no vector is committed."""
+        if self.name != "cfg2":
+            return None
+        try:
+            z = np.load(os.path.join(ROOT, "tests", "golden", "batch_vectors.npz"))
+        except Exception:
+            return None
+        lo, hi = rank * self.B, (rank + 1) * self.B
+        if hi > z["traj/pose"].shape[0] or tuple(int(v) for v in z["traj/pso"]) != (self.P, self.I):
+            return None
+        return z["traj/pose"][lo:hi], z["traj/cost"][lo:hi]
 
 
-def workload_name(batch):
-    """config.workload of both arms (the reference arm runs a bounded sample of the same workload)."""
-    return (f"cfg2 shape (configs[1]; batched as configs[2]): {batch} independent 1081-beam scan-matches per GPU vs "
-            "50 m/0.5 m NDT maps (one dense table per problem), 70 particles x 50 iterations")
+def scanset_of(workload, cs, f):
+    from ndtpso_slam_b200 import synthetic as syn
+    return syn.trajectory_problem(syn.CFG2 if workload == "cfg2" else syn.CFG5[cs], f)
+
+
+def make_problem(workload, cs, f, sparse=False):
+    from ndtpso_slam_b200 import frames
+    return frames.problem_from_scans(scanset_of(workload, cs, f), sparse=sparse, seed=1 + f)
+
+
+def parity_stats(pose, cost, want_pose, want_cost):
+    pose, want_pose = np.asarray(pose).reshape(-1, 3), np.asarray(want_pose).reshape(-1, 3)
+    cost, want_cost = np.asarray(cost).reshape(-1), np.asarray(want_cost).reshape(-1)
+    dp = np.abs(pose - want_pose).max(axis=1) if len(pose) else np.zeros(0)
+    ds = np.where(cost == want_cost, 0.0, np.abs(cost - want_cost) / np.maximum(np.abs(want_cost), 1e-300)) if len(cost) else np.zeros(0)
+    return {"n_checked": int(len(dp)), "max_abs_dpose": float(dp.max()) if len(dp) else 0.0,
+            "max_rel_dscore": float(ds.max()) if len(ds) else 0.0, "bit_exact_poses": int((dp == 0).sum())}
 
 
 # ------------------------------------------------------------------------------------------
@@ -150,82 +215,95 @@ class ClockSampler:
 # CPU arm: the reference's own implementation on the host cores
 # ------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    kind, scan_args, seeds = args
-    from ndtpso_slam_b200 import synthetic as syn
+    """Solves the given problems of the workload one after the other on one thread; returns (seconds spent in the solves,
+    pose[n, 3], cost[n]).  Map building is outside the timed part (the GPU arm's batches are built before its clock starts too)."""
+    kind, workload, P, I, specs = args
     from oracle import binding
-    ss = syn.trajectory_problem(syn.CFG2, scan_args)
-    t0 = time.perf_counter()
+    poses, costs, secs = [], [], 0.0
     if kind == "reference":
         R = binding.Reference()
-        rf, q = R.build_problem(ss)
-        rf.build()
-        t0 = time.perf_counter()
-        for s in seeds:
-            R.pso(rf, q, ss.guess, ss.deviation, P, I, seed=s, num_threads=1)
+        built = []
+        for cs, f in specs:
+            ss = scanset_of(workload, cs, f)
+            rf, q = R.build_problem(ss)
+            rf.build()
+            built.append((ss, rf, q, f))
+        for ss, rf, q, f in built:
+            t0 = time.perf_counter()
+            pose, _ = R.pso(rf, q, ss.guess, ss.deviation, P, I, seed=1 + f, num_threads=1)
+            secs += time.perf_counter() - t0
+            poses.append(pose)
+            costs.append(R.cost(rf, q, pose))
     else:
-        from ndtpso_slam_b200 import workload
-        flat = workload.cfg2_batch(1, first=scan_args)[0]
         O = binding.Oracle()
-        t0 = time.perf_counter()
-        for s in seeds:
-            O.pso(flat, flat["guess"], flat["deviation"], P, I, seed=s)
-    return time.perf_counter() - t0
+        flats = [make_problem(workload, cs, f) for cs, f in specs]
+        for fl in flats:
+            t0 = time.perf_counter()
+            pose, cost, _ = O.pso(fl, fl["guess"], fl["deviation"], P, I, seed=fl["seed"])
+            secs += time.perf_counter() - t0
+            poses.append(pose)
+            costs.append(cost)
+    return secs, np.array(poses).reshape(-1, 3), np.array(costs)
 
 
-def cpu_reference_rate(matches_per_worker):
-    """matches/s of the reference CPU path using every host core: nproc single-thread workers over
-    disjoint problems (its deterministic mode; in-process outer parallelism is impossible because
-    the reference draws from the process-global rand()).  Also times the as-shipped OpenMP mode."""
+def cpu_reference_rate(wl, matches_per_worker, as_shipped=True):
+    """matches/s of the reference CPU path using every host core: nproc single-thread workers over disjoint problems (its
+    deterministic mode; in-process outer parallelism is impossible because the reference draws from the process-global rand()).
+    The problems are the GPU batch's own first ones (rank 0's, wrapping around), so the results double as a live parity check:
+    returns (baseline dict, specs solved, pose, cost).  Also times the as-shipped OpenMP mode."""
     from oracle import binding
     kind = "reference" if os.path.exists(binding.REF_SO) else "port"
     if kind == "port":
         binding.build()
-    cores = os.cpu_count() or 1
-    jobs = [(kind, w, list(range(1 + w * 1000, 1 + w * 1000 + matches_per_worker))) for w in range(cores)]
-    t0 = time.perf_counter()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    own = wl.specs(0, 1)
+    specs = [own[i % len(own)] for i in range(cores * matches_per_worker)]
+    jobs = [(kind, wl.name, wl.P, wl.I, specs[w * matches_per_worker:(w + 1) * matches_per_worker]) for w in range(cores)]
     with mp.get_context("spawn").Pool(cores) as pool:
-        pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    # wall includes process start-up and map building; use the slowest worker's solve time instead
-    with mp.get_context("spawn").Pool(cores) as pool:
-        per = pool.map(_cpu_worker, jobs)
+        res = pool.map(_cpu_worker, jobs)
+    per = [r[0] for r in res]
     rate = cores * matches_per_worker / max(per)
-    out = {"value": rate, "unit": "scan-matches/s", "cores": cores, "kind": kind,
-           "sample": f"{cores} single-thread workers x {matches_per_worker} cfg2 matches each (70x50, 1081 pts), slowest worker {max(per):.2f} s",
+    out = {"value": rate, "unit": "scan-matches/s", "cores": cores, "kind": kind, "per_core": rate / cores,
+           "sample": f"{cores} single-thread workers x {matches_per_worker} matches each = the batch's own first {min(len(specs), len(own))} problems "
+                     f"({wl.P}x{wl.I}, 1081 pts), slowest worker {max(per):.2f} s",
            "single_thread_ms_per_match": 1e3 * float(np.median(per)) / matches_per_worker}
-    if kind == "reference":
-        from ndtpso_slam_b200 import synthetic as syn
+    if kind == "reference" and as_shipped:
         R = binding.Reference()
-        ss = syn.trajectory_problem(syn.CFG2, 0)
+        cs, f = own[0]
+        ss = scanset_of(wl.name, cs, f)
         rf, q = R.build_problem(ss)
-        ts = [R.pso(rf, q, ss.guess, ss.deviation, P, I, seed=s, num_threads=-1)[1] for s in range(1, 9)]
+        # torchrun exports OMP_NUM_THREADS=1, and pso_optimization itself lowers the team size whenever num_threads limits it
+        # (core.cpp:75-79): put it back to the cores this process may use before timing the as-shipped mode
+        R.lib.ref_omp_set_num_threads(cores)
+        ts = [R.pso(rf, q, ss.guess, ss.deviation, wl.P, wl.I, seed=s, num_threads=-1)[1] for s in range(1, 9)]
         out["as_shipped_openmp"] = {"value": 1.0 / float(np.median(ts[2:])), "unit": "scan-matches/s", "threads": R.lib.ref_omp_max_threads(),
                                     "note": "num_threads=-1 inside one match; non-deterministic result (SURVEY.md section 0.5)"}
-    return out, wall
+    return out, specs, np.concatenate([r[1] for r in res]), np.concatenate([r[2] for r in res])
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    wl = Workload(args.workload, args.batch)
     per_step = max(1, args.ref_matches)
     rates = []
     base = None
     t_all = time.perf_counter()
     for step in range(args.warmup + args.steps):
-        base, _ = cpu_reference_rate(per_step)
+        base, _, _, _ = cpu_reference_rate(wl, per_step, as_shipped=(step == 0))
         if step >= args.warmup:
             rates.append(base["value"])
         if time.perf_counter() - t_all > 240:
             break
     value = float(np.mean(rates)) if rates else base["value"]
     base["value"] = value
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": args.gpus, "steps": len(rates),
+    base["per_core"] = value / base["cores"]
+    base["rate_spread"] = [float(min(rates)), float(max(rates))] if rates else None
+    line = {"impl": "reference", "metric": wl.metric, "value": value, "unit": "scan-matches/s", "n_gpus": args.gpus, "steps": len(rates),
             "warmup": args.warmup, "ms_per_step": 1e3 * base["cores"] * per_step / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch), "batch_per_gpu": args.batch, "particles": P, "iterations": I,
-                       "sample": f"each step: {base['cores']} x {per_step} matches of that workload (its first trajectory problems, own map "
-                                 "each) on the host cores, one single-thread worker per core"},
+            "config": {"workload": wl.describe(), "batch_per_gpu": wl.B, "particles": wl.P, "iterations": wl.I},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "scan-matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -235,14 +313,15 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def measured_traffic(batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of pso_sliced_kernel per launch, from the committed
-    `ncu --set full` capture of this workload (profiles/); None for a batch size that was not captured."""
+def measured_profile(workload, batch):
+    """Per-launch counters of pso_sliced_kernel from the committed `ncu --set full` capture of this workload (profiles/traffic.json):
+    {"dram_bytes": dram__bytes_read.sum + dram__bytes_write.sum, "shared_wavefronts": l1tex__data_pipe_lsu_wavefronts_mem_shared.sum};
+    {} for a workload / batch size that was not captured."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(str(batch))
+        return json.load(open(path)).get(f"{workload}:{batch}", {})
     except Exception:
-        return None
+        return {}
 
 
 def measured_peaks():
@@ -349,9 +428,10 @@ def _run_gpu_arm(args, real_stdout):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.batch
+    wl = Workload(args.workload, args.batch)
+    B, P, I = wl.B, wl.P, wl.I
 
-    flats = make_problems(B, rank)
+    flats = wl.problems(rank, world)
     ctx = capi.Context(local)
     stream = torch.cuda.Stream()  # a real (non-legacy) stream shared by torch events, NCCL and the library
     torch.cuda.set_stream(stream)
@@ -359,18 +439,16 @@ def _run_gpu_arm(args, real_stdout):
     conf = capi.PsoConfig.make(population=P, iterations=I)
 
     # pinned host copies of every input array (the e2e path copies from these every step)
-    pinned_flats, h2d_bytes = [], 0
+    pinned_flats = []
     for f in flats:
         g = dict(f)
         for k in ("points", "mean", "inv_cov", "built"):
             t = torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory()
             g[k] = t.numpy()
             g["_keep_" + k] = t
-            h2d_bytes += t.numel() * t.element_size()
         pinned_flats.append(g)
     pset = capi.ProblemSet(pinned_flats)
-    h2d_bytes += B * (48 + 4)  # guess, deviation, seed
-    d2h_bytes = B * 32
+    table_bytes = sum(f["mean"].nbytes + f["inv_cov"].nbytes + f["built"].nbytes for f in flats)
 
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -383,12 +461,11 @@ def _run_gpu_arm(args, real_stdout):
     # batch of 256 CTAs leaves 40 of the 296 CTA slots empty and drains unevenly, and with the next step on the other
     # stream its CTAs take the free slots at once.  Every step is a full pass of the hot path over one batch (K0 table
     # compaction, K1 rand() streams, K2 PSO, result exchange for N > 1); four copies are cycled so that what a step
-    # touches (~41 MB) has been pushed out of the 126 MB L2 by the three steps in between.  The single-stream, L2-flushed form is measured beside it (`single_stream`), and the
-    # roofline uses that form's kernel durations.
-    NCOPY = 4  # resident copies of the batch, used round-robin: 4 x ~41 MB touched per step (compact tables, rand streams, flags) > 126 MB of L2
+    # touches has been pushed out of the 126 MB L2 by the three steps in between.  The single-stream, L2-flushed form is
+    # measured beside it (`single_stream`).
+    NCOPY = 4
     streams = [stream, torch.cuda.Stream()]
     bts = [ctx.batch(pset, conf) for _ in range(NCOPY)]
-    bt = bts[0]
     res_ts = [None] * NCOPY
     if world > 1:
         for i in range(NCOPY):
@@ -429,6 +506,7 @@ def _run_gpu_arm(args, real_stdout):
             with torch.cuda.stream(st):
                 sharding.gather_results(res_ts[i].view(B, 4), world * B, world, rank)
 
+    gathered = None
     if ex is not None:  # once: the fused exchange delivers exactly what the collective delivers
         resident_step(0)
         class _ExG:
@@ -438,6 +516,7 @@ def _run_gpu_arm(args, real_stdout):
         ref_rows = sharding.gather_results(res_ts[0].view(B, 4), world * B, world, rank)
         torch.cuda.synchronize()
         assert torch.equal(fused, ref_rows), "fused exchange and NCCL all-gather disagree"
+        gathered = fused.cpu().numpy()
 
     # single stream, L2 flushed between steps (not timed): per-step CUDA events
     n_single = max(3, min(args.steps, 10))
@@ -455,7 +534,7 @@ def _run_gpu_arm(args, real_stdout):
     single_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     kt = bts[0].kernel_times_ms()  # last solve: K0, K1, K2, not overlapped with anything
 
-    # the timed region: K steps alternating between the two copies / streams
+    # the timed region: K steps cycling the copies / streams
     for k in range(max(args.warmup, NCOPY)):
         resident_step(k % NCOPY)
     barrier()
@@ -472,16 +551,42 @@ def _run_gpu_arm(args, real_stdout):
     barrier()
     launches = ctx.launch_count() - launches0
     total_ms = float(ev_start.elapsed_time(ev_end))
+
+    # sustained: the same loop for at least --sustain-seconds (not fewer steps than the timed region)
+    n_sus = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / max(total_ms / args.steps, 1e-3))))
+    barrier()
+    ev_s0, ev_s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_s0.record(streams[0])
+    for k in range(n_sus):
+        resident_step(k % NCOPY)
+        if (k & 63) == 63:
+            streams[(k + 1) & 1].synchronize()  # keep the host a bounded number of launches ahead
+    streams[0].wait_stream(streams[1])
+    ev_s1.record(streams[0])
+    barrier()
+    sus_ms = float(ev_s0.elapsed_time(ev_s1))
     if world > 1:
-        t = torch.tensor([total_ms, single_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, single_ms, sus_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, single_ms = float(t[0].item()), float(t[1].item())
+        total_ms, single_ms, sus_ms = (float(v) for v in t.tolist())
     ctx.set_stream(streams[0].cuda_stream)
     pose, cost = bts[0].results()
     for i in range(1, NCOPY):
         pose1, cost1 = bts[i].results()
         assert np.array_equal(pose, pose1) and np.array_equal(cost, cost1), "the resident copies disagree"
-    stats = bts[0].stats()
+    stats = bts[0].stats_ex().astype(np.float64)
+    if gathered is not None:  # what the exchange delivered to this rank is what every rank computed
+        assert np.array_equal(gathered[rank * B:(rank + 1) * B, :3], pose) and np.array_equal(gathered[rank * B:(rank + 1) * B, 3], cost)
+
+    # ---- parity of the timed batch, every problem of every rank, against the unmodified reference's golden vectors
+    gold = wl.golden(rank, world)
+    par = parity_stats(pose, cost, gold[0], gold[1]) if gold is not None else parity_stats(np.zeros((0, 3)), np.zeros(0), np.zeros((0, 3)), np.zeros(0))
+    if world > 1:
+        t = torch.tensor([par["max_abs_dpose"], par["max_rel_dscore"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([par["n_checked"], par["bit_exact_poses"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        par = {"n_checked": int(c[0].item()), "max_abs_dpose": float(t[0].item()), "max_rel_dscore": float(t[1].item()), "bit_exact_poses": int(c[1].item())}
 
     # ---- e2e arm: host buffers in, host poses out, every step.  Throughput form of the public API:
     # ndtpso_align_submit (stage + H2D + launches) / ndtpso_align_collect (D2H + sync), several batches in
@@ -493,9 +598,8 @@ def _run_gpu_arm(args, real_stdout):
     depth = max(1, args.e2e_depth)
 
     def e2e_steps(n):
-        # `depth` batches in flight: with two, the GPU holds a single batch while the host stages and uploads the next one
-        # (0.6 + 0.3 ms of every 2.2 ms step: 117 k matches/s); with three it always has two batches queued on its two
-        # streams and the end-to-end rate equals the resident one (tools/e2e_depth.py)
+        # `depth` batches in flight: with two, the GPU holds a single batch while the host stages and uploads the next one;
+        # with three it always has two batches queued on its two streams (tools/e2e_depth.py)
         tickets, out = collections.deque(), None
         for _ in range(n):
             tickets.append(ctx.align_submit(pset, conf))
@@ -531,7 +635,7 @@ def _run_gpu_arm(args, real_stdout):
 
     # ---- configs[1] read literally: ONE scan-match at a time (thread-block-cluster form of the kernel)
     single = None
-    if rank == 0:
+    if rank == 0 and wl.name == "cfg2":
         one = capi.ProblemSet(pinned_flats[:1])
         b1 = ctx.batch(one, conf)
         ks = []
@@ -550,54 +654,96 @@ def _run_gpu_arm(args, real_stdout):
 
     # ---- the per-scan callback with the maps resident in HBM: loadLaser -> align -> update
     tracking = None
-    if rank == 0 and not args.no_tracking:
+    if rank == 0 and wl.name == "cfg2" and not args.no_tracking:
         tracking = run_tracking(B, conf, steps=max(4, min(args.steps, 12)), device=local, groups=args.tracking_groups)
 
+    rc = 0
     if rank == 0:
         peaks, peak_src = measured_peaks()
         value = world * B * args.steps / (total_ms * 1e-3)
         e2e = world * B * args.steps / e2e_s
+        alg_bytes, alg_flop = wl.alg_bytes(), wl.alg_flop()
         # dominant kernel: K2.  Its launches overlap in the timed region (two streams), so its effective duration per launch
         # is its share of the step time there; the isolated duration (single stream, nothing else running) is given beside it.
         k2_share = float(kt[2]) / float(kt.sum())
         k2_s = k2_share * (total_ms / args.steps) * 1e-3
         k2_iso_s = float(kt[2]) * 1e-3
-        ach_gbs = ALG_BYTES_PER_MATCH * B / k2_s / 1e9
-        ach_tf = ALG_FLOP_PER_MATCH * B / k2_s / 1e12
+        ach_gbs = alg_bytes * B / k2_s / 1e9
+        ach_tf = alg_flop * B / k2_s / 1e12
+        prof = measured_profile(wl.name, B)
+        sm_clock = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        wavefronts = prof.get("shared_wavefronts")
+        smem_pipe = None
+        if wavefronts:
+            n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+            smem_pipe = {"resource": "shared-memory data pipe (l1tex__data_pipe_lsu_wavefronts_mem_shared): one wavefront per SM per clock",
+                         "wavefronts_per_launch": wavefronts, "peak_wavefronts_per_s": n_sm * sm_clock,
+                         "frac": wavefronts / k2_s / (n_sm * sm_clock), "frac_isolated": wavefronts / k2_iso_s / (n_sm * sm_clock),
+                         "note": "wavefronts from the committed ncu capture (profiles/traffic.json), duration measured in this run; the kernel's "
+                                 "cell lookups (2 + 16 + 8 bytes per lane and evaluation = 6.6 wavefronts per warp) are what fills this pipe"}
         line = {
-            "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": wl.metric, "value": value, "unit": "scan-matches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(B),
+            "config": {"workload": wl.describe(),
                        "batch_per_gpu": B, "particles": P, "iterations": I,
-                       "l2": "inputs larger than L2: four resident copies of the batch (4 x 130 MB of dense tables, of which a step touches ~41 MB: "
-                             "built flags, built cells, compact tables, rand streams) are used round-robin, 164 MB between two uses of a copy",
+                       "l2": f"inputs larger than L2: four resident copies of the batch (4 x {table_bytes / 1e6:.0f} MB of dense tables; a step touches the built "
+                             "flags, the built cells, its compact tables and rand streams) are used round-robin, three other steps between two uses of a copy",
                        "pipelining": "step k runs on copy k % 4 and stream k & 1, so consecutive steps overlap while one drains",
                        "collective": exchange_kind},
+            "sustained": {"value": world * B * n_sus / (sus_ms * 1e-3), "unit": "scan-matches/s", "steps": n_sus, "seconds": sus_ms * 1e-3,
+                          "note": "the timed loop kept running back to back; clocks are sampled over the timed region, this leg and the e2e arm"},
             "e2e": {"value": e2e, "unit": "scan-matches/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "api": f"ndtpso_align_submit/collect, {depth} batches in flight",
                     "one_call_sync": world * B * args.steps / e2e_sync_s},
+            "parity": dict(par, pose_atol=POSE_ATOL, score_rtol=SCORE_RTOL,
+                           against=("the unmodified reference's pose and cost_function value for every problem of the timed batch on every rank "
+                                    "(tests/golden/batch_vectors.npz, made by tests/golden/make_golden_batch.py)") if gold is not None else
+                                   "no committed vectors for this workload: see `live`"),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "pso_sliced_kernel", "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": measured_traffic(B), "peak_source": peak_src,
+                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": prof.get("dram_bytes"), "peak_source": peak_src,
                          "launch_ms": k2_s * 1e3, "launch_ms_note": "K2's share (%.1f %%) of the step time in the timed region, where launches overlap" % (100 * k2_share),
+                         "algorithmic_bytes_per_match": alg_bytes, "algorithmic_flop_per_match": alg_flop,
+                         "fp64_achieved_tflops": ach_tf, "fp64_peak_tflops": fp64_peak, "fp64_frac": ach_tf / fp64_peak,
+                         "isolated_ms": float(kt[2]), "isolated_achieved_gbs": alg_bytes * B / k2_iso_s / 1e9,
+                         "isolated_frac": alg_bytes * B / k2_iso_s / 1e9 / peaks["hbm_gbs"],
+                         "smem_pipe_frac": smem_pipe["frac"] if smem_pipe else None,
                          "kernel_ms": {"compact_map": float(kt[0]), "rng_fill": float(kt[1]), "pso": float(kt[2])},
-                         "isolated": {"pso_ms": float(kt[2]), "achieved_gbs": ALG_BYTES_PER_MATCH * B / k2_iso_s / 1e9,
-                                      "fp64_tflops": ALG_FLOP_PER_MATCH * B / k2_iso_s / 1e12,
-                                      "note": "one launch alone on the GPU (single stream): 256 CTAs fill 86 % of the 296 CTA slots"},
+                         "isolated": {"pso_ms": float(kt[2]), "achieved_gbs": alg_bytes * B / k2_iso_s / 1e9,
+                                      "fp64_tflops": alg_flop * B / k2_iso_s / 1e12,
+                                      "note": "one launch alone on the GPU (single stream)"},
                          "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                                  "note": "algorithmic flops (31 per point-evaluation x the 3571 cost evaluations a match makes in the reference); peak = DFMA probe on this GPU. The fp32 screen settles ~86 % of those evaluations without touching the fp64 pipe, so this is work delivered per second, not pipe utilisation (ncu: profiles/)"}},
+                                  "note": "algorithmic flops (31 per point-evaluation x the cost evaluations a match makes in the reference); peak = DFMA probe on this GPU. The fp32 screen settles most of those evaluations without touching the fp64 pipe, so this is work delivered per second, not pipe utilisation (ncu: profiles/)"},
+                         "binding": smem_pipe},
             "single_stream": {"value": world * B * n_single / (single_ms * 1e-3), "unit": "scan-matches/s", "ms_per_step": single_ms / n_single,
                               "note": "one resident batch, one stream, L2 flushed (256 MiB write) between steps, per-step CUDA events"},
             "single_match": single,
             "tracking": tracking,
-            "rounds_per_match": float(stats[:, 0].mean()), "pose0": [float(v) for v in pose[0]],
+            "per_match": {"rounds": float(stats[:, 0].mean()), "gbest_updates": float(stats[:, 1].mean()), "fp64_evaluations": float(stats[:, 2].mean()),
+                          "settled_by_fp32_screen": float(stats[:, 3].mean())},
+            "pose0": [float(v) for v in pose[0]],
         }
         if not args.no_cpu:
-            line["cpu_baseline"], _ = cpu_reference_rate(args.ref_matches)
+            base, specs, cpose, ccost = cpu_reference_rate(wl, args.ref_matches)
+            line["cpu_baseline"] = base
+            # live parity: the reference (or the oracle port) just solved the batch's own first problems with the batch's seeds
+            own = wl.specs(0, world)
+            idx = [own.index(sp) for sp in specs if sp in own]
+            keep = [i for i, sp in enumerate(specs) if sp in own]
+            line["parity"]["live"] = dict(parity_stats(pose[idx], cost[idx], cpose[keep], ccost[keep]),
+                                          against=f"oracle/_ref ({base['kind']}) run by this bench's cpu_baseline leg on the same problems and seeds")
+        ok = line["parity"]["max_abs_dpose"] <= POSE_ATOL and line["parity"]["max_rel_dscore"] <= SCORE_RTOL
+        live = line["parity"].get("live")
+        if live:
+            ok = ok and live["max_abs_dpose"] <= POSE_ATOL and live["max_rel_dscore"] <= SCORE_RTOL
+        line["parity"]["ok"] = bool(ok)
+        rc = 0 if ok else 3
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        if not ok:
+            print("bench.py: PARITY FAILURE (see the line's `parity`)", file=sys.stderr)
     if world > 1:
         dist.barrier()
         for e_ in exs:
@@ -605,7 +751,7 @@ def _run_gpu_arm(args, real_stdout):
                 e_.close()
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 def main():
@@ -613,16 +759,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="scan-match problems per GPU per step")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2: BASELINE.json's headline (configs[1..3]); cfg5: configs[4], the multi-resolution sweep")
+    ap.add_argument("--batch", type=int, default=0, help="scan-match problems per GPU per step (default 256; 148 for cfg5)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-matches", type=int, default=4, help="CPU arm: matches per host worker per step")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-matches", type=int, default=0, help="CPU arm: matches per host worker per step (default 16 for cfg2, 2 for cfg5)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and the live parity check it feeds)")
     ap.add_argument("--no-tracking", action="store_true", help="skip the device-resident tracking leg")
     ap.add_argument("--tracking-groups", type=int, default=3, help="tracking leg: independent groups of robots served by their own host thread and stream")
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e arm: batches kept in flight through ndtpso_align_submit/collect")
+    ap.add_argument("--sustain-seconds", type=float, default=2.2, help="length of the sustained leg")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N > 1: how the solved poses reach every rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.batch <= 0:
+        args.batch = 256 if args.workload == "cfg2" else 148
+    if args.ref_matches <= 0:
+        args.ref_matches = 16 if args.workload == "cfg2" else 2
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

@@ -132,8 +132,8 @@ enum {
   NDTPSO_OPT_PIPELINE_CHUNKS = 7,  /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4; default 0 = auto: 3 from 128 problems on) */
   NDTPSO_OPT_EXCHANGE_TIMEOUT_MS = 8, /* ndtpso_exchange_wait: give up after this long (default 10000) */
   NDTPSO_OPT_HOT_CHUNK = 9, /* point-sliced kernel: particles speculated per round while gbest improves often; -1 auto, 0 = whole swarm */
-  NDTPSO_OPT_SCREEN = 10    /* point-sliced kernel: fp32 lower-bound screen before the fp64 cost (results identical either way); -1 auto (not when its
-                               tables would cost the second CTA per SM), 0 off, 1 on whenever the batch qualifies */
+  NDTPSO_OPT_SCREEN = 10    /* point-sliced kernel: fp32 lower-bound screen before the fp64 cost (results identical either way); -1 / 1 on
+                               whenever the batch qualifies and its tables fit shared memory, 0 off */
 };
 int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value);
 

@@ -61,7 +61,7 @@ struct ndtpso_ctx {
   int opt_kernel = 0;  // 0 auto, 1 warp-per-particle (generic), 2 point-sliced
   int opt_npt = 0;     // points per thread of the sliced kernel, 0 auto
   int opt_chunks = 0;      // pipelined align_batch: number of chunks (1 = off, 0 = auto: 3 from 128 problems on)
-  int opt_screen = -1;     // fp32 screening of the sliced kernel: -1 auto (on when the batch qualifies and it does not cost the second CTA per SM), 0 off, 1 on whenever the batch qualifies
+  int opt_screen = -1;     // fp32 screening of the sliced kernel: -1 / 1 on whenever the batch qualifies and its tables fit shared memory, 0 off
   int opt_hot_chunk = -1;  // speculation window of the sliced kernel while gbest improves often: -1 auto, 0 off
   int opt_cand_batch = 0;  // candidates scored together by the sliced kernel: 0 auto (largest), 1, 2, 4
   int64_t launches = 0;
@@ -813,12 +813,23 @@ int launch_sliced(ndtpso_batch* bt) {
   nw = std::max(nw, 4);
   PsoParams probe{};
   bool scr = screen_params(bt, &probe);
-  const int smem_plain = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, 0));
-  int smem = round16(sliced_smem_bytes(bt->prm.P, nw, 0, bt->max_table_smem, scr ? bt->max_n_rec + 1 : 0));
-  // not at the price of the second CTA per SM, and not beyond what a CTA may have
-  if (scr && (smem > ctx->max_smem_optin || (ctx->opt_screen < 0 && smem > ctx->max_smem_optin / 2 && smem_plain <= ctx->max_smem_optin / 2))) {
+  auto smem_of = [&](int warps, bool screen) { return round16(sliced_smem_bytes(bt->prm.P, warps, 0, bt->max_table_smem, screen ? bt->max_n_rec + 1 : 0)); };
+  int smem = smem_of(nw, scr);
+  if (scr && smem > ctx->max_smem_optin) {  // the screen's tables do not fit: fp64 only
     scr = false;
-    smem = smem_plain;
+    smem = smem_of(nw, false);
+  }
+  if (ctx->opt_npt <= 0 && ctx->opt_warps <= 0 && smem > ctx->max_smem_optin / 2) {
+    // one CTA per SM anyway (large swarm or table: BASELINE configs[4], 200 particles): registers are plentiful then, so take
+    // the shape with the most warps that fits (tools/cfg5_time.py: 2 points x 17 warps 7.5 ms, 3 x 12 warps 8.0 ms per 148 matches)
+    for (int p2 = 1; p2 < npt; ++p2) {
+      const int w2 = std::max((n + 32 * p2 - 1) / (32 * p2), 4);
+      if (w2 > kSlicedMaxWarps[p2] || smem_of(w2, scr) > ctx->max_smem_optin) continue;
+      npt = p2;
+      nw = w2;
+      smem = smem_of(nw, scr);
+      break;
+    }
   }
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;

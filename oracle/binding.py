@@ -227,6 +227,8 @@ class Reference:
                                C.POINTER(C.c_double)]
         L.ref_align.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_double)]
         L.ref_omp_max_threads.restype = C.c_int
+        L.ref_omp_set_num_threads.argtypes = [C.c_int]
+        L.ref_omp_set_num_threads.restype = None
         L.ref_sizeof_cell.restype = C.c_int
 
     def frame(self, **kw) -> RefFrame:

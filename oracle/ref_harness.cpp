@@ -178,6 +178,9 @@ void ref_glir(void* ref, void* cur, const double* guess, const double* dev, int 
 }
 
 int ref_omp_max_threads(void) { return omp_get_max_threads(); }
+// pso_optimization calls omp_set_num_threads(n) whenever PSOConfig::num_threads limits it (core.cpp:75-79), which lowers what
+// omp_get_max_threads() reports from then on: a later "all threads" run needs the team size put back.
+void ref_omp_set_num_threads(int n) { omp_set_num_threads(n); }
 
 int ref_sizeof_cell(void) { return static_cast<int>(sizeof(NDTCell)); }
 

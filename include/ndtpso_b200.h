@@ -132,6 +132,7 @@ enum {
   NDTPSO_OPT_PIPELINE_CHUNKS = 7,  /* ndtpso_align_batch: chunks staged/uploaded/solved on separate streams (1..4; default 0 = auto: 3 from 128 problems on) */
   NDTPSO_OPT_EXCHANGE_TIMEOUT_MS = 8, /* ndtpso_exchange_wait: give up after this long (default 10000) */
   NDTPSO_OPT_HOT_CHUNK = 9, /* point-sliced kernel: particles speculated per round while gbest improves often; -1 auto, 0 = whole swarm */
+  NDTPSO_OPT_HOST_THREADS = 11, /* host threads (caller included) that stage this context's batches; 0 = auto: the cores the process may use, at most 8 */
   NDTPSO_OPT_SCREEN = 10    /* point-sliced kernel: fp32 lower-bound screen before the fp64 cost (results identical either way); -1 / 1 on
                                whenever the batch qualifies and its tables fit shared memory, 0 off */
 };
@@ -224,6 +225,37 @@ void* ndtpso_exchange_device_results(ndtpso_exchange* ex);
 /* wait + D2H + synchronise: out_pose [world * n_per_rank][3], out_cost [world * n_per_rank]; either may be NULL */
 int ndtpso_exchange_results(ndtpso_exchange* ex, double* out_pose, double* out_cost);
 void ndtpso_exchange_destroy(ndtpso_exchange* ex);
+
+/* ---- several GPUs behind one call: single process, one context per device ------------------------ */
+/* The path shards over independent problems: device g of G gets the contiguous block
+ * [g*ceil(n/G), min(n, (g+1)*ceil(n/G))).  A C or C++ caller — the node that calls NDTFrame::align
+ * (src/ndtpso_slam_node.cpp:194), or a batch replay tool — hands over all n problems in one call; every device
+ * stages, uploads and solves its shard concurrently (one host thread and one staging pool per device), and the
+ * results come back in problem order.  Results are bit-identical to the single-GPU entry points. */
+typedef struct ndtpso_multi ndtpso_multi;
+typedef struct ndtpso_multi_batch ndtpso_multi_batch;
+/* devices: n_devices CUDA ordinals, or NULL for 0 .. n_devices-1; n_devices <= NDTPSO_MAX_RANKS */
+int ndtpso_multi_create(const int32_t* devices, int32_t n_devices, ndtpso_multi** out);
+void ndtpso_multi_destroy(ndtpso_multi* m);
+int32_t ndtpso_multi_size(const ndtpso_multi* m);
+ndtpso_ctx* ndtpso_multi_ctx(ndtpso_multi* m, int32_t i); /* device i's context (options, launch counts) */
+const char* ndtpso_multi_last_error(const ndtpso_multi* m);
+/* ndtpso_align_batch over all devices: host buffers in, host buffers out */
+int ndtpso_align_batch_multi(ndtpso_multi* m, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf,
+                             double* out_pose /* [n][3] */, double* out_cost /* [n] */);
+/* the throughput form (ndtpso_align_submit / ndtpso_align_collect): keep three batches in flight */
+int ndtpso_align_submit_multi(ndtpso_multi* m, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_multi_batch** out);
+int ndtpso_align_collect_multi(ndtpso_multi_batch* batch, double* out_pose /* [n][3] */, double* out_cost /* [n] */);
+/* the shards kept resident in HBM (ndtpso_batch_create / _solve).  When n is a multiple of the device count the shards'
+ * results are also exchanged on the device side, fused into the PSO kernel's epilogue (ndtpso_exchange_*, connected with
+ * ndtpso_exchange_connect_local): after a solve EVERY device holds all n results. */
+int ndtpso_multi_batch_create(ndtpso_multi* m, int32_t n, const ndtpso_problem* problems, const ndtpso_pso_config* conf, ndtpso_multi_batch** out);
+int ndtpso_multi_batch_solve(ndtpso_multi_batch* batch);   /* asynchronous launches on every device */
+int ndtpso_multi_batch_results(ndtpso_multi_batch* batch, double* out_pose /* [n][3] */, double* out_cost /* [n] */); /* synchronises */
+/* device pointer, on device i, to the gathered [n][4] fp64 results of the last solve (NULL unless the shards are exchanged);
+ * valid after ndtpso_multi_batch_results or after synchronising device i's context */
+void* ndtpso_multi_batch_device_results(ndtpso_multi_batch* batch, int32_t i);
+void ndtpso_multi_batch_destroy(ndtpso_multi_batch* batch);
 
 /* ---- device self-measurement (roofline denominators MEASURED_PEAKS.json lacks) --- */
 /* Sustained fp64 FMA throughput of this GPU in TFLOP/s (2 flop per DFMA). */

@@ -18,6 +18,7 @@ OPT_WARPS_PER_CTA, OPT_SMEM_BYTES, OPT_CLUSTER, OPT_KERNEL, OPT_POINTS_PER_THREA
 OPT_EXCHANGE_TIMEOUT_MS = 8
 OPT_HOT_CHUNK = 9
 OPT_SCREEN = 10
+OPT_HOST_THREADS = 11
 KERNEL_AUTO, KERNEL_WARP_PER_PARTICLE, KERNEL_POINT_SLICED = 0, 1, 2
 
 #: every symbol include/ndtpso_b200.h declares
@@ -28,6 +29,9 @@ EXPORTS = [
     "ndtpso_batch_stats", "ndtpso_batch_stats_ex", "ndtpso_batch_kernel_times", "ndtpso_batch_destroy", "ndtpso_ctx_launch_count", "ndtpso_ctx_last_transfer_bytes", "ndtpso_ctx_synchronize", "ndtpso_measure_fp64_peak",
     "ndtpso_exchange_create", "ndtpso_exchange_connect", "ndtpso_exchange_connect_local", "ndtpso_batch_attach_exchange", "ndtpso_exchange_wait",
     "ndtpso_exchange_device_results", "ndtpso_exchange_results", "ndtpso_exchange_destroy",
+    "ndtpso_multi_create", "ndtpso_multi_destroy", "ndtpso_multi_size", "ndtpso_multi_ctx", "ndtpso_multi_last_error", "ndtpso_align_batch_multi",
+    "ndtpso_align_submit_multi", "ndtpso_align_collect_multi", "ndtpso_multi_batch_create", "ndtpso_multi_batch_solve", "ndtpso_multi_batch_results",
+    "ndtpso_multi_batch_device_results", "ndtpso_multi_batch_destroy",
 ]
 IPC_HANDLE_BYTES, MAX_RANKS = 64, 8
 
@@ -120,6 +124,25 @@ def load_library(build_if_missing: bool = True):
     L.ndtpso_exchange_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndtpso_exchange_destroy.argtypes = [C.c_void_p]
     L.ndtpso_exchange_destroy.restype = None
+    L.ndtpso_multi_create.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+    L.ndtpso_multi_destroy.argtypes = [C.c_void_p]
+    L.ndtpso_multi_destroy.restype = None
+    L.ndtpso_multi_size.argtypes = [C.c_void_p]
+    L.ndtpso_multi_size.restype = C.c_int32
+    L.ndtpso_multi_ctx.argtypes = [C.c_void_p, C.c_int32]
+    L.ndtpso_multi_ctx.restype = C.c_void_p
+    L.ndtpso_multi_last_error.argtypes = [C.c_void_p]
+    L.ndtpso_multi_last_error.restype = C.c_char_p
+    L.ndtpso_align_batch_multi.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.c_void_p, C.c_void_p]
+    L.ndtpso_align_submit_multi.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
+    L.ndtpso_align_collect_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ndtpso_multi_batch_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Problem), C.POINTER(PsoConfig), C.POINTER(C.c_void_p)]
+    L.ndtpso_multi_batch_solve.argtypes = [C.c_void_p]
+    L.ndtpso_multi_batch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ndtpso_multi_batch_device_results.argtypes = [C.c_void_p, C.c_int32]
+    L.ndtpso_multi_batch_device_results.restype = C.c_void_p
+    L.ndtpso_multi_batch_destroy.argtypes = [C.c_void_p]
+    L.ndtpso_multi_batch_destroy.restype = None
     _lib = L
     return L
 
@@ -362,6 +385,99 @@ class Context:
     def close(self):
         if self.h:
             self.lib.ndtpso_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Multi:
+    """Several GPUs behind one call (include/ndtpso_b200.h: ndtpso_multi_*): a single process, one context per device, the
+    problems split into contiguous shards.  `devices`: CUDA ordinals (one context each; an ordinal may repeat)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.ndtpso_multi_create(devs, len(devices), C.byref(h))
+        if rc != OK:
+            raise NdtpsoError(rc, "ndtpso_multi_create failed (no CUDA device? the product has no CPU path)")
+        self.h = h
+        self.size = len(devices)
+
+    def _check(self, rc):
+        if rc != OK:
+            raise NdtpsoError(rc, (self.lib.ndtpso_multi_last_error(self.h) or b"").decode())
+
+    def set_option(self, option: int, value: int):
+        for i in range(self.size):
+            rc = self.lib.ndtpso_ctx_set_option(self.lib.ndtpso_multi_ctx(self.h, i), option, int(value))
+            if rc != OK:
+                raise NdtpsoError(rc, "ndtpso_ctx_set_option failed")
+
+    def launch_count(self) -> int:
+        return sum(int(self.lib.ndtpso_ctx_launch_count(self.lib.ndtpso_multi_ctx(self.h, i))) for i in range(self.size))
+
+    def align_batch(self, flats, conf: PsoConfig):
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        pose, cost = np.empty((ps.n, 3)), np.empty(ps.n)
+        self._check(self.lib.ndtpso_align_batch_multi(self.h, ps.n, ps.array, C.byref(conf), _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def align_submit(self, flats, conf: PsoConfig):
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        t = C.c_void_p()
+        self._check(self.lib.ndtpso_align_submit_multi(self.h, ps.n, ps.array, C.byref(conf), C.byref(t)))
+        return (t, ps)
+
+    def align_collect(self, ticket):
+        t, ps = ticket
+        pose, cost = np.empty((ps.n, 3)), np.empty(ps.n)
+        self._check(self.lib.ndtpso_align_collect_multi(t, _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def batch(self, flats, conf: PsoConfig) -> "MultiBatch":
+        ps = flats if isinstance(flats, ProblemSet) else ProblemSet(flats)
+        return MultiBatch(self, ps, conf)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ndtpso_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBatch:
+    """Shards resident in HBM, one per device; with equal shards every device also ends up with all results (fused exchange)."""
+
+    def __init__(self, multi: Multi, ps: ProblemSet, conf: PsoConfig):
+        self.multi, self.ps = multi, ps
+        h = C.c_void_p()
+        multi._check(multi.lib.ndtpso_multi_batch_create(multi.h, ps.n, ps.array, C.byref(conf), C.byref(h)))
+        self.h = h
+
+    def solve(self):
+        self.multi._check(self.multi.lib.ndtpso_multi_batch_solve(self.h))
+
+    def results(self):
+        pose, cost = np.empty((self.ps.n, 3)), np.empty(self.ps.n)
+        self.multi._check(self.multi.lib.ndtpso_multi_batch_results(self.h, _ptr(pose), _ptr(cost)))
+        return pose, cost
+
+    def device_results_ptr(self, i: int):
+        return self.multi.lib.ndtpso_multi_batch_device_results(self.h, int(i))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.multi.lib.ndtpso_multi_batch_destroy(self.h)
             self.h = None
 
     def __del__(self):

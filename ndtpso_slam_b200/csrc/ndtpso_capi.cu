@@ -46,8 +46,14 @@ inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a
 
 }  // namespace
 
+namespace {
+class HostPool;
+}
+
 struct ndtpso_ctx {
   int device = 0;
+  HostPool* pool = nullptr;  // this context's staging workers (created on first use)
+  int opt_host_threads = 0;  // staging threads incl. the caller: 0 = auto (the cores this process may use, at most 8)
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // pipelined align_batch
@@ -215,17 +221,37 @@ int validate_problem(ndtpso_ctx* ctx, const ndtpso_problem& p, int b) {
 }
 
 // Persistent host workers for the staging loops (table scans, gathers, memcpy): spawning threads per batch cost more than
-// the loops themselves once several ranks share a host.  One pool per process; run() hands out indices in small chunks,
-// the calling thread works too, and calls are serialised (contexts of one process stage one batch at a time).
+// the loops themselves.  One pool per CONTEXT, created on first use: contexts of one process (one per GPU, ndtpso_multi) stage
+// their shards concurrently, each on its own workers.  run() hands out indices in small chunks and the calling thread works too.
 class HostPool {
  public:
-  static HostPool& instance() {
-    static HostPool pool;
-    return pool;
+  explicit HostPool(int threads) {
+    // Threads incl. the caller: the cores this process may use, at most 8; NDTPSO_HOST_THREADS or NDTPSO_OPT_HOST_THREADS
+    // override.  Not divided by the ranks sharing the host: on a 32-core host with 8 ranks, 4 threads per rank staged
+    // slower than 8 oversubscribed ones (e2e 704 k vs 807 k scan-matches/s on 8 GPUs).
+    int budget = threads;
+    if (budget <= 0) {
+      int hw = (int)std::thread::hardware_concurrency();
+      cpu_set_t set;
+      if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
+      budget = std::min(8, std::max(1, hw));
+      if (const char* e = std::getenv("NDTPSO_HOST_THREADS")) budget = std::max(1, std::min(64, std::atoi(e)));
+    }
+    const int nw = std::max(0, std::min(63, budget - 1));
+    for (int t = 0; t < nw; ++t) workers_.emplace_back([this] { loop(); });
   }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int threads() const { return (int)workers_.size() + 1; }
   template <class F>
-  void run(int n, int max_threads, F f) {
-    const int want = std::min<int>(std::min<int>(max_threads, (int)workers_.size() + 1), n / 8);  // not worth a thread for fewer than 8 items
+  void run(int n, F f) {
+    const int want = std::min<int>((int)workers_.size() + 1, n / 8);  // not worth a thread for fewer than 8 items
     if (want <= 1) {
       for (int i = 0; i < n; ++i) f(i);
       return;
@@ -249,26 +275,6 @@ class HostPool {
   }
 
  private:
-  HostPool() {
-    // Threads this process may use for staging: the cores it may run on, at most 8 with the caller; NDTPSO_HOST_THREADS
-    // overrides.  Not divided by the ranks sharing the host: on a 32-core host with 8 ranks, 4 threads per rank staged
-    // slower than 8 oversubscribed ones (e2e 704 k vs 807 k scan-matches/s on 8 GPUs).
-    int hw = (int)std::thread::hardware_concurrency();
-    cpu_set_t set;
-    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
-    int budget = std::max(1, hw);
-    if (const char* e = std::getenv("NDTPSO_HOST_THREADS")) budget = std::max(1, std::min(64, std::atoi(e)));
-    const int nw = std::max(0, std::min(7, budget - 1));
-    for (int t = 0; t < nw; ++t) workers_.emplace_back([this] { loop(); });
-  }
-  ~HostPool() {
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      stop_ = true;
-    }
-    cv_.notify_all();
-    for (auto& w : workers_) w.join();
-  }
   void work(std::function<void(int)>& fn, int n) {
     for (;;) {
       const int i0 = next_.fetch_add(4);
@@ -307,35 +313,32 @@ class HostPool {
   bool stop_ = false;
 };
 
-// Runs f(i) for i in [0, n) on up to `max_threads` host threads (staging is memcpy/scan bound).
+// Runs f(i) for i in [0, n) on the context's staging workers (staging is memcpy / gather bound).
 template <class F>
-void parallel_for(int n, int max_threads, F f) {
-  HostPool::instance().run(n, max_threads, f);
+void parallel_for(ndtpso_ctx* ctx, int n, F f) {
+  if (!ctx->pool) ctx->pool = new HostPool(ctx->opt_host_threads);
+  ctx->pool->run(n, f);
 }
 
-// What the host learns from one pass over a table: which cells are built, the grid rows they
-// span (=> shared-memory need of the compact form), and whether Sigma^-1 is symmetric.
+// What the host learns from the first pass over a table — the `built` flags only (sequential, 1 byte per cell): which cells
+// are built and the grid rows they span (=> shared-memory need of the compact form).  Whether every Sigma^-1 is symmetric,
+// finite and positive semi-definite is checked while the rows are copied (check_row), the one pass that touches them.
 struct MapScan {
   std::vector<int> cells;  // built cell indices, ascending (dense input); empty for sparse input
   int n_rec = 0, row0 = 0, nrows = 0;
   bool symmetric = true, ok = true;  // symmetric: also finite and positive semi-definite
 };
 
+// S01 == S10 bit for bit, finite, positive semi-definite (NaN/inf fail the comparisons): what NDTCell::build produces, and
+// what the point-sliced kernel assumes (its exponent is then <= 0)
+inline bool check_row(const double* S, const double* mu) {
+  return memcmp(&S[1], &S[2], sizeof(double)) == 0 && S[0] >= 0. && S[3] >= 0. && S[0] * S[3] - S[1] * S[2] >= 0. && S[0] < 1e300 && S[3] < 1e300 &&
+         std::isfinite(mu[0]) && std::isfinite(mu[1]);
+}
+
 void scan_map(const ndtpso_map_view& m, bool want_cells, MapScan* out) {
   const int ncells = m.w_cells * m.h_cells;
-  int ay = INT_MAX, by = -1, n_rec = 0;
-  auto note = [&](int cell, size_t row) {
-    const int iy = cell / m.w_cells;
-    ay = std::min(ay, iy);
-    by = std::max(by, iy);
-    ++n_rec;
-    const double* S = &m.inv_cov[4 * row];
-    if (memcmp(&S[1], &S[2], sizeof(double)) != 0) out->symmetric = false;
-    // finite and positive semi-definite (NaN/inf fail the comparisons): the sliced kernel's exponent is then <= 0
-    if (!(S[0] >= 0. && S[3] >= 0. && S[0] * S[3] - S[1] * S[2] >= 0. && S[0] < 1e300 && S[3] < 1e300 && std::isfinite(m.mean[2 * row]) &&
-          std::isfinite(m.mean[2 * row + 1])))
-      out->symmetric = false;
-  };
+  int lo = INT_MAX, hi = -1, n_rec = 0;
   if (m.n_sparse >= 0) {
     for (int r = 0; r < m.n_sparse; ++r) {
       const int cell = m.cell_index[r];
@@ -343,7 +346,11 @@ void scan_map(const ndtpso_map_view& m, bool want_cells, MapScan* out) {
         out->ok = false;
         return;
       }
-      note(cell, (size_t)r);
+    }
+    n_rec = m.n_sparse;
+    if (n_rec) {
+      lo = m.cell_index[0];
+      hi = m.cell_index[n_rec - 1];
     }
   } else {
     if (want_cells) out->cells.reserve(1024);
@@ -354,19 +361,23 @@ void scan_map(const ndtpso_map_view& m, bool want_cells, MapScan* out) {
       if (!w) continue;
       for (int k = 0; k < 8; ++k)
         if (m.built[c + k]) {
-          note(c + k, (size_t)(c + k));
+          lo = std::min(lo, c + k);
+          hi = c + k;
+          ++n_rec;
           if (want_cells) out->cells.push_back(c + k);
         }
     }
     for (; c < ncells; ++c)
       if (m.built[c]) {
-        note(c, (size_t)c);
+        lo = std::min(lo, c);
+        hi = c;
+        ++n_rec;
         if (want_cells) out->cells.push_back(c);
       }
   }
   out->n_rec = n_rec;
-  out->row0 = n_rec ? ay : 0;
-  out->nrows = n_rec ? by - ay + 1 : 0;
+  out->row0 = n_rec ? lo / m.w_cells : 0;  // cells ascend, so the first and last built cell give the row span
+  out->nrows = n_rec ? hi / m.w_cells - out->row0 + 1 : 0;
 }
 
 // Builds the arena for `n` problems and fills the pinned staging copy.
@@ -420,11 +431,10 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     map_of[b] = it->second;
   }
   const int M = (int)maps.size();
-  constexpr int kHostThreads = 8;
 
   // ---- one pass over every table
   std::vector<MapScan> scans(M);
-  parallel_for(M, kHostThreads, [&](int i) { scan_map(*maps[i], compact_on_host, &scans[i]); });
+  parallel_for(ctx, M, [&](int i) { scan_map(*maps[i], compact_on_host, &scans[i]); });
   for (int i = 0; i < M; ++i)
     if (!scans[i].ok) return fail(ctx, NDTPSO_ERR_ARG, "sparse map: cell_index must be strictly ascending and inside the grid");
 
@@ -502,9 +512,9 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   // ---- fill the staging buffer (tables and scans in parallel: pure memcpy / gather)
   DevMap* hm = reinterpret_cast<DevMap*>(h + o_maps);
   std::vector<int> map_dyn(M, 0);
-  parallel_for(M, kHostThreads, [&](int i) {
+  parallel_for(ctx, M, [&](int i) {
     const ndtpso_map_view& m = *maps[i];
-    const MapScan& sc = scans[i];
+    MapScan& sc = scans[i];
     const int ncells = m.w_cells * m.h_cells;
     DevMap dm{};
     dm.x_min = m.x_min;
@@ -528,6 +538,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
     dm.rec = reinterpret_cast<double*>(d + o_rec[i]);
     dm.hdr = reinterpret_cast<int*>(d + o_hdr[i]);
     hm[i] = dm;
+    bool regular = true;
     if (m.n_sparse >= 0 || !staged_sparse[i]) {  // as given
       if (rows[i]) {
         memcpy(h + o_mean[i], m.mean, (size_t)rows[i] * 16);
@@ -535,20 +546,35 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
       }
       if (m.n_sparse >= 0) {
         if (rows[i]) memcpy(h + o_cidx[i], m.cell_index, (size_t)rows[i] * 4);
+        for (int r = 0; r < rows[i]; ++r) regular = regular && check_row(m.inv_cov + 4 * (size_t)r, m.mean + 2 * (size_t)r);
       } else {
         memcpy(h + o_built[i], m.built, (size_t)ncells);
+        for (int c = 0; c < ncells; ++c)
+          if (m.built[c]) regular = regular && check_row(m.inv_cov + 4 * (size_t)c, m.mean + 2 * (size_t)c);
       }
-    } else {  // dense -> sparse on the host
+    } else {  // dense -> sparse on the host: the one pass over the built rows (scattered in the caller's table, so the rows of
+              // the cells a few steps ahead are prefetched while the current one is copied and checked)
       double* hmean = reinterpret_cast<double*>(h + o_mean[i]);
       double* hicov = reinterpret_cast<double*>(h + o_icov[i]);
       int* hcidx = reinterpret_cast<int*>(h + o_cidx[i]);
+      constexpr int kAhead = 12;
+      for (int r = 0; r < std::min(kAhead, sc.n_rec); ++r) {
+        __builtin_prefetch(m.mean + 2 * (size_t)sc.cells[r]);
+        __builtin_prefetch(m.inv_cov + 4 * (size_t)sc.cells[r]);
+      }
       for (int r = 0; r < sc.n_rec; ++r) {
+        if (r + kAhead < sc.n_rec) {
+          __builtin_prefetch(m.mean + 2 * (size_t)sc.cells[r + kAhead]);
+          __builtin_prefetch(m.inv_cov + 4 * (size_t)sc.cells[r + kAhead]);
+        }
         const size_t c = (size_t)sc.cells[r];
         hcidx[r] = (int)c;
         memcpy(hmean + 2 * (size_t)r, m.mean + 2 * c, 16);
         memcpy(hicov + 4 * (size_t)r, m.inv_cov + 4 * c, 32);
+        regular = regular && check_row(hicov + 4 * (size_t)r, hmean + 2 * (size_t)r);
       }
     }
+    sc.symmetric = regular;
     map_dyn[i] = (sc.n_rec + 1) * 48 + round16((sc.nrows * m.w_cells + 1) * 2);
   });
   for (int i = 0; i < M; ++i) {
@@ -567,7 +593,7 @@ int batch_build(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problems, cons
   }
   DevProblem* hp = reinterpret_cast<DevProblem*>(h + o_probs);
   std::vector<double> pmax_of(std::max(n, 1), 0.);
-  parallel_for(n, kHostThreads, [&](int b) {
+  parallel_for(ctx, n, [&](int b) {
     const ndtpso_problem& p = problems[b];
     DevProblem dp{};
     dp.pts = reinterpret_cast<const double2*>(d + o_pts[b]);
@@ -998,6 +1024,7 @@ void ndtpso_ctx_destroy(ndtpso_ctx* ctx) {
   for (auto& ps : ctx->pipe_stream)
     if (ps) cudaStreamDestroy(ps);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx->pool;
   delete ctx;
 }
 
@@ -1044,6 +1071,14 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
       if (value < 1 || value > 600000) return fail(ctx, NDTPSO_ERR_ARG, "exchange timeout must be in 1..600000 ms");
       ctx->opt_exchange_timeout_ms = value;
       return NDTPSO_OK;
+    case NDTPSO_OPT_HOST_THREADS:
+      if (value < 0 || value > 64) return fail(ctx, NDTPSO_ERR_ARG, "host threads must be in 0..64 (0 = auto)");
+      if (ctx->pool && (int)value != ctx->opt_host_threads) {  // takes effect with the next batch
+        delete ctx->pool;
+        ctx->pool = nullptr;
+      }
+      ctx->opt_host_threads = (int)value;
+      return NDTPSO_OK;
     case NDTPSO_OPT_SMEM_BYTES:
       if (value < 0 || value > ctx->max_smem_optin) return fail(ctx, NDTPSO_ERR_ARG, "shared memory bytes out of range");
       ctx->opt_smem = value;
@@ -1069,6 +1104,7 @@ int ndtpso_ctx_last_transfer_bytes(const ndtpso_ctx* ctx, int64_t* h2d, int64_t*
 
 int ndtpso_ctx_synchronize(ndtpso_ctx* ctx) {
   if (!ctx) return NDTPSO_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NDTPSO_OK;
 }
@@ -1144,6 +1180,7 @@ int ndtpso_batch_results(ndtpso_batch* bt, double* out_pose, double* out_cost) {
   ndtpso_ctx* ctx = bt->ctx;
   if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_results before batch_solve");
   if (bt->n == 0) return NDTPSO_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));  // a process with one context per GPU calls in from any thread
   // results come back through the (already consumed) head of the pinned staging buffer
   double* h = static_cast<double*>(bt->pin.ptr);
   if (bt->results_enqueued) {
@@ -1168,6 +1205,7 @@ int ndtpso_batch_stats(ndtpso_batch* bt, int32_t* out) {
   if (!bt || !out) return NDTPSO_ERR_ARG;
   ndtpso_ctx* ctx = bt->ctx;
   if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_stats before batch_solve");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   std::vector<int32_t> all((size_t)kStatsWords * bt->n);
   CUDA_TRY(ctx, cudaMemcpy(all.data(), bt->d_stats, sizeof(int) * kStatsWords * (size_t)bt->n, cudaMemcpyDeviceToHost));
@@ -1182,6 +1220,7 @@ int ndtpso_batch_stats_ex(ndtpso_batch* bt, int32_t* out) {
   if (!bt || !out) return NDTPSO_ERR_ARG;
   ndtpso_ctx* ctx = bt->ctx;
   if (!bt->solved) return fail(ctx, NDTPSO_ERR_ARG, "batch_stats before batch_solve");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(ctx, cudaMemcpy(out, bt->d_stats, sizeof(int) * kStatsWords * (size_t)bt->n, cudaMemcpyDeviceToHost));
   return NDTPSO_OK;
@@ -1567,4 +1606,5 @@ int ndtpso_measure_fp64_peak(ndtpso_ctx* ctx, double* out_tflops) {
 
 }  // extern "C"
 
+#include "ndtpso_multi_host.inc"
 #include "ndtpso_dframes_host.inc"

@@ -754,6 +754,83 @@ def _run_gpu_arm(args, real_stdout):
     return rc
 
 
+def run_single_process_arm(args):
+    """`--single-process`: all N GPUs from ONE process through ndtpso_multi_* (include/ndtpso_b200.h) — the form a C/C++ caller
+    uses.  value: the shards resident in HBM, one stream per device, the fused exchange delivering every result to every device,
+    wall clock around K steps (each step ends with every device synchronised); e2e: ndtpso_align_submit_multi / _collect_multi with
+    pinned host buffers, three batches in flight."""
+    import torch
+
+    from ndtpso_slam_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    G = args.gpus
+    wl = Workload(args.workload, args.batch)
+    B, P, I = wl.B, wl.P, wl.I
+    flats = [f for r in range(G) for f in wl.problems(r, G)]  # shard r of the multi object = rank r's problems
+    for f in flats:
+        for k in ("points", "mean", "inv_cov", "built"):
+            t = torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory()
+            f["_keep_" + k], f[k] = t, t.numpy()
+    pset = capi.ProblemSet(flats)
+    conf = capi.PsoConfig.make(population=P, iterations=I)
+    m = capi.Multi(list(range(G)))
+    bt = m.batch(pset, conf)
+    for _ in range(args.warmup):
+        bt.solve()
+    pose, cost = bt.results()
+    sampler = ClockSampler(0)
+    sampler.start()
+    n0 = m.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bt.solve()
+    bt.results()
+    wall = time.perf_counter() - t0
+    launches = m.launch_count() - n0
+    exchanged = bt.device_results_ptr(0) is not None
+    bt.close()
+    depth = max(1, args.e2e_depth)
+
+    def e2e_steps(n):
+        tickets, out = collections.deque(), None
+        for _ in range(n):
+            tickets.append(m.align_submit(pset, conf))
+            if len(tickets) >= depth:
+                out = m.align_collect(tickets.popleft())
+        while tickets:
+            out = m.align_collect(tickets.popleft())
+        return out
+
+    e2e_steps(2 * depth)
+    t0 = time.perf_counter()
+    ep, ec = e2e_steps(args.steps)
+    e2e_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.align_batch(pset, conf)
+    sync_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.array_equal(ep, pose) and np.array_equal(ec, cost), "e2e and resident paths disagree"
+    gold = [wl.golden(r, G) for r in range(G)]
+    par = parity_stats(pose, cost, np.concatenate([g[0] for g in gold]), np.concatenate([g[1] for g in gold])) if all(g is not None for g in gold) \
+        else parity_stats(np.zeros((0, 3)), np.zeros(0), np.zeros((0, 3)), np.zeros(0))
+    par["ok"] = bool(par["max_abs_dpose"] <= POSE_ATOL and par["max_rel_dscore"] <= SCORE_RTOL)
+    h2d = sum(f["points"].nbytes for f in flats)  # lower bound: the scans; the built cells' rows come on top (see the per-process line)
+    line = {"metric": wl.metric, "value": G * B * args.steps / wall, "unit": "scan-matches/s", "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.describe(), "batch_per_gpu": B, "particles": P, "iterations": I,
+                       "process_model": f"single process, ndtpso_multi_* over {G} devices (one context, host thread and staging pool per device)",
+                       "collective": "fused device-side exchange between the shards (ndtpso_exchange_connect_local)" if exchanged else "host gather",
+                       "l2": "one resident copy per device, single stream (the per-process arm cycles four copies on two streams)"},
+            "e2e": {"value": G * B * args.steps / e2e_s, "unit": "scan-matches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(G * B * 32),
+                    "api": f"ndtpso_align_submit_multi/_collect_multi, {depth} batches in flight", "one_call_sync": G * B * args.steps / sync_s},
+            "parity": par, "gpu_launches": int(launches), "clocks": clocks, "pose0": [float(v) for v in pose[0]]}
+    print(json.dumps(line))
+    m.close()
+    return 0 if par["ok"] else 3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -769,6 +846,7 @@ def main():
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e arm: batches kept in flight through ndtpso_align_submit/collect")
     ap.add_argument("--sustain-seconds", type=float, default=2.2, help="length of the sustained leg")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N > 1: how the solved poses reach every rank")
+    ap.add_argument("--single-process", action="store_true", help="drive all --gpus devices from this one process through ndtpso_multi_* (not under torchrun)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.batch <= 0:
@@ -777,6 +855,8 @@ def main():
         args.ref_matches = 16 if args.workload == "cfg2" else 2
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.single_process:
+        return run_single_process_arm(args)
     return run_gpu_arm(args)
 
 

@@ -80,8 +80,9 @@ enum {
 /* how ndtpso_dframes_align draws its random numbers */
 enum {
   NDTPSO_RNG_SEEDED = 0,    /* srand(seeds[b]) before every align: the batch mode of ndtpso_b200.h */
-  NDTPSO_RNG_CONTINUE = 1   /* the reference as shipped: never seeded, every frame owns one glibc rand()
+  NDTPSO_RNG_CONTINUE = 1,  /* the reference as shipped: never seeded, every frame owns one glibc rand()
                                stream (default seed 1) that continues across align calls */
+  NDTPSO_RNG_HOST = 2       /* the numbers are the caller's: ndtpso_dframes_align_streams */
 };
 
 void ndtpso_dframes_config_default(ndtpso_dframes_config* cfg);
@@ -96,6 +97,10 @@ int64_t ndtpso_dframes_device_bytes(const ndtpso_dframes* df);
  * a frame whose trans isZero(1e-6) is not transformed (ndtframe.cpp:151-153). */
 int ndtpso_dframes_load_laser(ndtpso_dframes* df, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
                               float range_max, const double* scan_trans);
+/* The same for a scan frame of cell side `scan_cell_side` (<= 0: one cell of the frame's size), whatever the object's
+ * scan_cell_side: the drop-in NDTFrame passes the cell side of the frame the caller loaded the scan into. */
+int ndtpso_dframes_load_laser_binned(ndtpso_dframes* df, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
+                                     float range_max, const double* scan_trans, double scan_cell_side);
 /* The same state set directly: points_xy [n_frames][stride_points][2] host, n_points [n_frames]. */
 int ndtpso_dframes_set_scan_points(ndtpso_dframes* df, const double* points_xy, const int32_t* n_points, int32_t stride_points);
 
@@ -114,6 +119,12 @@ int ndtpso_dframes_build(ndtpso_dframes* df);
 int ndtpso_dframes_align(ndtpso_dframes* df, const double* guess, const ndtpso_pso_config* conf, int32_t rng_mode,
                          const uint32_t* seeds /* [n_frames], NDTPSO_RNG_SEEDED only */, double* out_pose /* [n][3] */,
                          double* out_cost /* [n] */);
+
+/* The same with the random numbers drawn by the caller: rand_streams [n_frames][ndtpso_rand_draws(conf)] raw std::rand()
+ * outputs in call order.  This is what the drop-in NDTFrame::align uses: it draws from the process-global std::rand(), so a
+ * sequence of align() calls stays in lock-step with a CPU build of the reference whatever else the process does with rand(). */
+int ndtpso_dframes_align_streams(ndtpso_dframes* df, const double* guess, const ndtpso_pso_config* conf, const int32_t* rand_streams,
+                                 double* out_pose /* [n][3] */, double* out_cost /* [n] */);
 
 /* One pass of NDTPSONode::scan_matcher_ for every frame: loadLaser; on the first call the pose is
  * `initial_poses` (host [n][3], may be NULL = zero) and no matching is done (:188-192), afterwards

@@ -49,6 +49,14 @@ int ndtpso_frame_cost(ndtpso_frame* ref_frame, ndtpso_frame* new_frame, const do
 void ndtpso_frame_add_pose(ndtpso_frame* f, double timestamp, const double* pose /* [3] */);
 void ndtpso_frame_dump_map(ndtpso_frame* f, const char* filename);
 /* best cost of the most recent align */
+/* The map is mirrored in HBM (include/ndtpso_dframes.h) and ndtpso_frame_align / _update use the mirror: true for a frame
+ * that has been filled through ndtpso_frame_update only, from its first align on (see shim/include/ndtpso_slam/ndtframe.h). */
+int ndtpso_frame_device_resident(const ndtpso_frame* f);
+/* bytes the most recent align / update of this frame moved host->device through the mirror (0 without one) */
+void ndtpso_frame_last_h2d_bytes(const ndtpso_frame* f, int64_t* align_bytes, int64_t* update_bytes);
+/* the device's copy of the table (builds it first; synchronises): mean [C][2], inv_cov [C][4], built [C]; NDTPSO_ERR_ARG without a mirror */
+int ndtpso_frame_download_device_map(ndtpso_frame* f, double* mean, double* inv_cov, uint8_t* built);
+
 double ndtpso_frame_last_cost(void);
 const char* ndtpso_frame_last_error(void);
 

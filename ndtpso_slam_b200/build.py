@@ -28,7 +28,7 @@ def nvcc() -> str:
 
 SHIM = os.path.join(PKG, "shim")
 SHIM_LIB = os.path.join(LIB_DIR, "libndtpso_slam.so")
-SHIM_SOURCES = [os.path.join(SHIM, "src", f) for f in ("ndtcell.cpp", "ndtframe.cpp", "core.cpp", "frame_capi.cpp")]
+SHIM_SOURCES = [os.path.join(SHIM, "src", f) for f in ("ndtcell.cpp", "ndtframe.cpp", "ndtframe_device.cpp", "core.cpp", "frame_capi.cpp")]
 EIGEN_STANDIN = os.path.join(PKG, "..", "third_party", "eigen_standin")
 
 
@@ -44,7 +44,7 @@ def build_shim(force: bool = False) -> str:
     """libndtpso_slam.so: the drop-in NDTFrame / pso_optimization host library (g++, no FMA contraction,
     like the reference's build) linked against libndtpso_b200.so."""
     deps = SHIM_SOURCES + [os.path.join(SHIM, "include", "ndtpso_slam", f) for f in ("config.h", "core.h", "ndtcell.h", "ndtframe.h")]
-    deps += [os.path.join(PKG, "..", "include", "ndtpso_frames.h"), LIB_PATH]
+    deps += [os.path.join(PKG, "..", "include", f) for f in ("ndtpso_frames.h", "ndtpso_dframes.h", "ndtpso_b200.h")] + [LIB_PATH]
     if not force and os.path.exists(SHIM_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_LIB) for d in deps if os.path.exists(d)):
         return SHIM_LIB
     cmd = ["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(SHIM, "include"),

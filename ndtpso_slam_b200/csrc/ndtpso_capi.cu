@@ -688,10 +688,10 @@ int launch_pso(ndtpso_batch* bt, int smem) {
 //         side's own rounding as long as (pmax + W)/cs <= 2^22 (checked here).  pmax, W, 1/cs: the largest of the batch.
 //   beta: band around cell edges inside which fp32 and fp64 may pick different cells; it only has to be >= du, and is taken
 //         four times that, at least 5e-4.
-bool screen_params(const ndtpso_batch* bt, PsoParams* prm) {
+bool screen_params(const ndtpso_batch* bt, PsoParams* prm, bool ignore_option = false) {
   prm->screen = 0;
   const ndtpso_ctx* ctx = bt->ctx;
-  if (ctx->opt_screen == 0 || !bt->scr_ok || !(bt->scr_pmax <= 1e6) || !(bt->scr_ext > 0.) || bt->scr_gw >= (1 << 20)) return false;
+  if ((ctx->opt_screen == 0 && !ignore_option) || !bt->scr_ok || !(bt->scr_pmax <= 1e6) || !(bt->scr_ext > 0.) || bt->scr_gw >= (1 << 20)) return false;
   if (bt->max_n_rec + 1 > kScreenMaxRecords) return false;  // the staged grid holds 16-bit shared addresses of the screen's records
   const double u24 = 5.9604644775390625e-08;  // 2^-24
   const double pmax = std::max(bt->scr_pmax, 1.0), W = 2. * bt->scr_ext;
@@ -838,7 +838,9 @@ int launch_sliced(ndtpso_batch* bt) {
   if (npt < 1 || npt > kSlicedMaxNPT || nw > kSlicedMaxWarps[npt]) return 1;
   nw = std::max(nw, 4);
   PsoParams probe{};
-  bool scr = screen_params(bt, &probe);
+  // the launch shape is chosen as if the screen were on whenever the batch qualifies for it, whatever NDTPSO_OPT_SCREEN says:
+  // a cost is a tree sum over the CTA's warps, so only the same shape gives bit-identical costs with the screen on and off
+  bool scr = screen_params(bt, &probe, true);
   auto smem_of = [&](int warps, bool screen) { return round16(sliced_smem_bytes(bt->prm.P, warps, 0, bt->max_table_smem, screen ? bt->max_n_rec + 1 : 0)); };
   int smem = smem_of(nw, scr);
   if (scr && smem > ctx->max_smem_optin) {  // the screen's tables do not fit: fp64 only
@@ -856,6 +858,10 @@ int launch_sliced(ndtpso_batch* bt) {
       smem = smem_of(nw, scr);
       break;
     }
+  }
+  if (scr && ctx->opt_screen == 0) {  // switched off by the caller: same shape, without the screen's tables
+    scr = false;
+    smem = smem_of(nw, false);
   }
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;

@@ -404,8 +404,9 @@ __global__ void __launch_bounds__(kDfBuildThreads) frame_build_kernel(DevFrames 
 // ---- align bookkeeping ---------------------------------------------------------------------------
 // guess: [n][3] device or nullptr (= node_pose); seeds: [n] device or nullptr (= 1, the default
 // seed of a never-seeded process); rnd_base + b*rnd_stride = where K1 writes problem b's stream.
+// from_host: the streams were uploaded (drop-in mode: drawn from the process-global std::rand()), K1 skips these problems.
 __global__ void align_prepare_kernel(DevFrames F, const double* __restrict__ guess, const unsigned* __restrict__ seeds, int* rnd_base,
-                                     size_t rnd_stride) {
+                                     size_t rnd_stride, int from_host) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= F.n) return;
   DevProblem& pr = F.probs[b];
@@ -418,7 +419,7 @@ __global__ void align_prepare_kernel(DevFrames F, const double* __restrict__ gue
   F.s_iter[b] = it + 1;  // ndtframe.cpp:255
   pr.seed = seeds ? seeds[b] : 1u;
   pr.rnd = rnd_base + (size_t)b * rnd_stride;
-  pr.rnd_from_host = 0;
+  pr.rnd_from_host = from_host;
 }
 
 __global__ void align_finish_kernel(DevFrames F) {

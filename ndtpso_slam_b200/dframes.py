@@ -28,7 +28,7 @@ EXPORTS = [
     "ndtpso_dframes_load_laser", "ndtpso_dframes_set_scan_points", "ndtpso_dframes_update", "ndtpso_dframes_build",
     "ndtpso_dframes_align", "ndtpso_dframes_track_step", "ndtpso_dframes_download_map", "ndtpso_dframes_download_scan",
     "ndtpso_dframes_info", "ndtpso_dframes_status", "ndtpso_dframes_pso_stats", "ndtpso_dframes_kernel_times",
-    "ndtpso_dframes_attach_exchange",
+    "ndtpso_dframes_attach_exchange", "ndtpso_dframes_load_laser_binned", "ndtpso_dframes_align_streams",
 ]
 
 

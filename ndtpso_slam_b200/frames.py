@@ -54,6 +54,10 @@ def load_library():
     L.ndtpso_frame_add_pose.restype = None
     L.ndtpso_frame_dump_map.argtypes = [C.c_void_p, C.c_char_p]
     L.ndtpso_frame_dump_map.restype = None
+    L.ndtpso_frame_device_resident.argtypes = [C.c_void_p]
+    L.ndtpso_frame_last_h2d_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.ndtpso_frame_last_h2d_bytes.restype = None
+    L.ndtpso_frame_download_device_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndtpso_frame_last_cost.restype = C.c_double
     L.ndtpso_frame_last_error.restype = C.c_char_p
     _lib = L
@@ -64,6 +68,7 @@ def load_library():
 EXPORTS = ["ndtpso_frame_new", "ndtpso_frame_free", "ndtpso_frame_load_laser", "ndtpso_frame_update", "ndtpso_frame_build",
            "ndtpso_frame_is_built", "ndtpso_frame_reset_cells", "ndtpso_frame_map_view", "ndtpso_frame_sparse_map_view", "ndtpso_frame_scan_points",
            "ndtpso_frame_point_count", "ndtpso_frame_add_pose", "ndtpso_frame_dump_map", "ndtpso_frame_align", "ndtpso_frame_align_conf", "ndtpso_frame_glir", "ndtpso_frame_cost", "ndtpso_frame_last_cost",
+           "ndtpso_frame_device_resident", "ndtpso_frame_last_h2d_bytes", "ndtpso_frame_download_device_map",
            "ndtpso_frame_last_error"]
 
 
@@ -108,6 +113,27 @@ class Frame:
     @property
     def built(self) -> bool:
         return bool(self.lib.ndtpso_frame_is_built(self.h))
+
+    @property
+    def device_resident(self) -> bool:
+        """The map is mirrored in HBM and align/update go through the mirror."""
+        return bool(self.lib.ndtpso_frame_device_resident(self.h))
+
+    def last_h2d_bytes(self):
+        """(align, update): bytes the last align / update moved host->device through the mirror."""
+        a, u = C.c_int64(0), C.c_int64(0)
+        self.lib.ndtpso_frame_last_h2d_bytes(self.h, C.byref(a), C.byref(u))
+        return a.value, u.value
+
+    def device_map_table(self) -> dict:
+        """The device's copy of the dense table (mirrored frames only)."""
+        g = self._view(False)
+        n = g["w_cells"] * g["h_cells"]
+        mean, icov, built = np.zeros((n, 2)), np.zeros((n, 4)), np.zeros(n, dtype=np.uint8)
+        rc = self.lib.ndtpso_frame_download_device_map(self.h, mean.ctypes.data, icov.ctypes.data, built.ctypes.data)
+        if rc != 0:
+            raise capi.NdtpsoError(rc, "no device mirror")
+        return dict(mean=mean, inv_cov=icov, built=built)
 
     def add_pose(self, timestamp: float, pose):
         self.lib.ndtpso_frame_add_pose(self.h, float(timestamp), _d3(pose))

@@ -1,7 +1,16 @@
 // Drop-in NDTFrame: the class the reference's ROS node drives (src/ndtpso_slam_node.cpp:64-78,
 // 186-230) with the same constructor and method signatures as include/ndtpso_slam/ndtframe.h:31-72,
 // so the node recompiles against this header unchanged.  align() runs on the GPU through the C ABI
-// (include/ndtpso_b200.h); map building stays on the host.
+// (include/ndtpso_b200.h).
+//
+// The map lives in HBM.  A frame that is filled the way the node fills its reference frame — through update() only, from
+// the first point on — is mirrored by a device-resident frame (include/ndtpso_dframes.h): update() runs NDTFrame::update +
+// NDTCell::addPoint as a kernel, align() runs NDTFrame::build, the table compaction and the swarm there, and what crosses PCIe
+// per scan is the scan itself (4 bytes per beam when the scan frame was filled by one loadLaser call; NDTPSO_SHIM_EXACT_SCAN=1
+// sends the host-computed points, 16 bytes each, which keeps the device map bit-identical to the host's), the random numbers
+// and the pose.  The host keeps the points (dumpMap, pointCount) and its own copy of the table, built as often as the reference
+// builds its (NDTCell::build is not idempotent), so mapView() shows what the reference would hold.  A frame that receives points any other way (addPoint / loadLaser on the map itself, resetCells)
+// drops the mirror and uploads its table with every align, as before; the swarm runs on the GPU either way.
 //
 // Differences from the reference, all outside the node's use of the class:
 //  * `cells` is not a public vector<NDTCell>: storage is a dense (mean, Sigma^-1, built) table plus
@@ -77,6 +86,13 @@ class NDTFrame {
   double yMax() const { return s_y_max; }
   size_t pointCount() const;  // all windows of all cells
   int alignCalls() const { return s_iter; }
+  // ---- the device mirror
+  bool deviceResident() const;  // the map is mirrored in HBM and align() uses it
+  // bytes moved by the most recent align() / update() of this frame through the mirror (0 without one)
+  size_t lastAlignH2DBytes() const { return last_align_h2d_; }
+  size_t lastUpdateH2DBytes() const { return last_update_h2d_; }
+  // device copy of the table (synchronises): mean [numOfCells][2], inv_cov [numOfCells][4], built [numOfCells]; false without a mirror
+  bool downloadDeviceMap(double* mean, double* inv_cov, uint8_t* built);
 
  private:
   Vector3d s_trans{Vector3d::Zero()}, s_prev_pose{Vector3d::Zero()}, s_pose_diff{Vector3d::Zero()};
@@ -99,6 +115,26 @@ class NDTFrame {
   vector<double> sp_mean_, sp_icov_;
   mutable vector<Vector2d> scan_cache_;
   mutable bool scan_cache_valid_{false};
+
+  // ---- device mirror (ndtframe_device.cpp)
+  struct DeviceMirror;
+  DeviceMirror* dev_{nullptr};
+  bool mirror_ok_{true};     // false once a point entered the map by another way than update(), or the mirror failed
+  unsigned long version_{0}; // bumped by every change of this frame's points: identifies a scan for the mirror
+  // how this frame's points came to be, when by exactly one loadLaser into an empty frame: enough to redo it on the
+  // device from 4 bytes per beam
+  struct LaserInput {
+    vector<float> ranges;
+    float min_angle{0}, angle_increment{0}, max_range{0};
+    bool valid{false};
+  } laser_;
+  size_t last_align_h2d_{0}, last_update_h2d_{0};
+  void addPointInternal(Vector2d& point);
+  bool mirrorUpdate(const Vector3d& trans, const NDTFrame* new_frame, bool map_was_empty);
+  bool mirrorAlign(const Vector3d& guess, const NDTFrame* new_frame, const PSOConfig& conf, Vector3d* pose);
+  bool mirrorSyncScan(const NDTFrame* new_frame, size_t* h2d);
+  void dropMirror();
+  friend struct NDTFrameDeviceAccess;
 };
 
 #endif

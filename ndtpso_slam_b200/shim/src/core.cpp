@@ -28,6 +28,22 @@ ndtpso_ctx* context() {
   return g_ctx;
 }
 
+}  // namespace
+
+namespace ndtpso_b200 {
+// the process-wide context of the drop-in library; nullptr (no exception) without a usable CUDA device
+ndtpso_ctx* shim_context_or_null() {
+  try {
+    return context();
+  } catch (const std::exception&) {
+    return nullptr;
+  }
+}
+void shim_set_last_cost(double c) { g_last_cost = c; }
+}  // namespace ndtpso_b200
+
+namespace {
+
 void check(int rc, const char* what) {
   if (rc != NDTPSO_OK) throw std::runtime_error(std::string("ndtpso_b200: ") + what + ": " + ndtpso_last_error(g_ctx));
 }

@@ -104,6 +104,16 @@ void ndtpso_frame_add_pose(ndtpso_frame* f, double timestamp, const double* pose
   f->frame.addPose(timestamp, Vector3d(pose[0], pose[1], pose[2]));
 }
 void ndtpso_frame_dump_map(ndtpso_frame* f, const char* filename) { f->frame.dumpMap(filename, true, true, false); }
+int ndtpso_frame_device_resident(const ndtpso_frame* f) { return f->frame.deviceResident() ? 1 : 0; }
+void ndtpso_frame_last_h2d_bytes(const ndtpso_frame* f, int64_t* align_bytes, int64_t* update_bytes) {
+  if (align_bytes) *align_bytes = static_cast<int64_t>(f->frame.lastAlignH2DBytes());
+  if (update_bytes) *update_bytes = static_cast<int64_t>(f->frame.lastUpdateH2DBytes());
+}
+int ndtpso_frame_download_device_map(ndtpso_frame* f, double* mean, double* inv_cov, uint8_t* built) {
+  int ok = 0;
+  const int rc = guarded([&]() { ok = f->frame.downloadDeviceMap(mean, inv_cov, built) ? 1 : 0; });
+  return rc != NDTPSO_OK ? rc : (ok ? NDTPSO_OK : NDTPSO_ERR_ARG);
+}
 double ndtpso_frame_last_cost(void) { return pso_last_cost(); }
 const char* ndtpso_frame_last_error(void) { return g_err.c_str(); }
 

@@ -2,6 +2,7 @@
 // (lib/ndtpso_slam/ndtframe.cpp:19-66,144-235,240-266), scan matching on the GPU.
 #include "ndtpso_slam/ndtframe.h"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -32,7 +33,7 @@ NDTFrame::NDTFrame(Vector3d trans, unsigned short w, unsigned short h, double si
   slot_of_.assign(numOfCells, -1);
 }
 
-NDTFrame::~NDTFrame() = default;
+NDTFrame::~NDTFrame() { dropMirror(); }
 
 int NDTFrame::getCellIndex(Vector2d point, int grid_width, double side) {
   if (!((point.x() > s_x_min) && (point.x() < s_x_max) && (point.y() > s_y_min) && (point.y() < s_y_max))) return -1;  // strict
@@ -40,6 +41,24 @@ int NDTFrame::getCellIndex(Vector2d point, int grid_width, double side) {
 }
 
 void NDTFrame::addPoint(Vector2d& point) {
+  // a point added directly is not mirrored on the device: a mirrored map falls back to uploading its table per align
+  if (dev_ || zero_windows_) mirror_ok_ = false;
+  if (dev_) dropMirror();
+  laser_.valid = false;
+  addPointInternal(point);
+}
+
+namespace {
+// a process-wide counter: a scan frame that is deleted and re-allocated at the same address must not pass for the scan the
+// device already holds (the node does exactly that, ndtpso_slam_node.cpp:228-229)
+unsigned long next_version() {
+  static std::atomic<unsigned long> counter{0};
+  return ++counter;
+}
+}  // namespace
+
+void NDTFrame::addPointInternal(Vector2d& point) {
+  version_ = next_version();
   const int idx = getCellIndex(point, widthNumOfCells, cell_side);
   if (idx < 0 || static_cast<unsigned>(idx) >= numOfCells) return;
   int s = slot_of_[idx];
@@ -55,6 +74,9 @@ void NDTFrame::addPoint(Vector2d& point) {
 
 void NDTFrame::loadLaser(const vector<float>& laser_data, const float& min_angle, const float& angle_increment, const float& max_range) {
   built = false;
+  if (dev_ || zero_windows_) mirror_ok_ = false;  // a scan loaded into the map itself is not mirrored
+  if (dev_) dropMirror();
+  const bool first_fill = windows_.empty();
   const bool shift = !s_trans.isZero(1e-6);
   const unsigned n = static_cast<unsigned>(laser_data.size());
   for (unsigned i = 0; i < n; ++i) {
@@ -63,15 +85,30 @@ void NDTFrame::loadLaser(const vector<float>& laser_data, const float& min_angle
     const float theta = index_to_angle(i, angle_increment, min_angle);
     Vector2d p = laser_to_point(r, theta);
     if (shift) p = transform_point(p, s_trans);
-    addPoint(p);
+    addPointInternal(p);
+  }
+  // remembered so that a mirrored map can take this scan as 4 bytes per beam
+  laser_.valid = first_fill;
+  if (first_fill) {
+    laser_.ranges = laser_data;
+    laser_.min_angle = min_angle;
+    laser_.angle_increment = angle_increment;
+    laser_.max_range = max_range;
   }
 }
 
 void NDTFrame::update(Vector3d trans, NDTFrame* const new_frame) {
   built = false;
+  const bool map_was_empty = windows_.empty();
+  laser_.valid = false;
   for (const Vector2d& q : new_frame->scanPoints()) {  // slot 0 of every created cell, cell order (ndtframe.cpp:190-196)
     Vector2d p = transform_point(q, trans);
-    addPoint(p);
+    addPointInternal(p);
+  }
+  last_update_h2d_ = 0;
+  if (mirror_ok_ && zero_windows_ && !mirrorUpdate(trans, new_frame, map_was_empty)) {
+    mirror_ok_ = false;
+    dropMirror();
   }
 }
 
@@ -127,6 +164,7 @@ static void fill_geometry(const NDTFrame& f, ndtpso_map_view* out) {
 }
 
 void NDTFrame::mapView(ndtpso_map_view* out) const {
+  if (!built) const_cast<NDTFrame*>(this)->build();  // with the map mirrored on the device the host table is built on demand only
   fill_geometry(*this, out);
   out->mean = mean_.data();
   out->inv_cov = icov_.data();
@@ -136,6 +174,7 @@ void NDTFrame::mapView(ndtpso_map_view* out) const {
 }
 
 void NDTFrame::sparseMapView(ndtpso_map_view* out) const {
+  if (!built) const_cast<NDTFrame*>(this)->build();
   fill_geometry(*this, out);
   out->mean = sp_mean_.data();
   out->inv_cov = sp_icov_.data();
@@ -152,7 +191,20 @@ Vector3d NDTFrame::align(Vector3d initial_guess, const NDTFrame* const new_frame
   // spread of the initial swarm: fixed for the first two calls, then twice the last pose step (ndtframe.cpp:253)
   Vector3d deviation = s_iter < 2 ? Vector3d(.1, .1, 3.1415E-3) : (s_pose_diff * 2.).array().abs();
   ++s_iter;
-  Vector3d pose = pso_optimization(std::move(initial_guess), this, new_frame, deviation, conf);
+  Vector3d pose;
+  last_align_h2d_ = 0;
+  // cost_function builds the map lazily before the first evaluation (core.cpp:27-28).  NDTCell::build is not idempotent (every
+  // call re-adds the current slot's statistics), so the host's copy of the table is built here too, exactly as often as the
+  // reference's: it stays what the reference would hold, and what the device mirror holds.
+  if (!built) build();
+  // the mirror keeps its own copy of this bookkeeping and applies the same rule (align_prepare_kernel)
+  if (!(dev_ && mirror_ok_ && mirrorAlign(initial_guess, new_frame, conf, &pose))) {
+    if (dev_) {  // no mirror for this map (or it could not take this call): from here on the table is uploaded per align
+      mirror_ok_ = false;
+      dropMirror();
+    }
+    pose = pso_optimization(std::move(initial_guess), this, new_frame, deviation, conf);
+  }
   s_pose_diff = pose - s_prev_pose;
   s_prev_pose = pose;
   return pose;
@@ -165,6 +217,9 @@ void NDTFrame::addPose(double timestamp, const Vector3d& pose, const Vector3d& o
 }
 
 void NDTFrame::resetCells() {
+  if (dev_ || zero_windows_) mirror_ok_ = false;
+  if (dev_) dropMirror();
+  version_ = next_version();
   for (auto& w : windows_) w->reset();  // NDTCell::reset (ndtcell.cpp:80-91) leaves `built`, mean and Sigma^-1 as they are
   scan_cache_valid_ = false;            // the cached scan holds the points that were just dropped
 }

@@ -91,7 +91,7 @@ def test_dframes_header_exports_and_layout(lib):
     from ndtpso_slam_b200 import dframes
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ndtpso_dframes.h")).read(), flags=re.S)
     declared = sorted(set(re.findall(r"\b(ndtpso_dframes_[a-z0-9_]+)\s*\(", src)))
-    assert len(declared) == 17
+    assert len(declared) == 19
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ndtpso_dframes.h but not exported"
     assert sorted(dframes.EXPORTS) == declared

@@ -158,3 +158,83 @@ def test_align_with_explicit_config(golden, oracle):
     c = golden.case("cfg1")
     i = c["seeds"].index(3)
     assert np.abs(pose - c["pose"][i]).max() <= 1e-4
+
+
+def _callback_track(monkeypatch, exact, n_scans=8, P=30, I=20):
+    """The node's per-scan callback (ndtpso_slam_node.cpp:186-198) through the drop-in frames, on the golden track's scans."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "map_vectors.npz"))
+    monkeypatch.setenv("NDTPSO_SHIM_EXACT_SCAN", "1" if exact else "0")
+    from ndtpso_slam_b200 import capi
+    cfg, s = syn.CFG1, syn.CFG1.sensor
+    S = cfg.map_size_m
+    init = tuple(float(v) for v in z["track/initial"])
+    conf = capi.PsoConfig.make(population=P, iterations=I)
+    C.CDLL(None).srand(1)  # the golden track is that of a never-seeded process
+    ref = frames.Frame(width=S, height=S, cell_side=cfg.cell_side, calculate_cells_params=True)
+    cur = frames.Frame(trans=init, width=S, height=S, cell_side=cfg.cell_side, calculate_cells_params=False)
+    pose, out, h2d = np.array(init), [], []
+    for k, ranges in enumerate(z["track/ranges"][:n_scans]):
+        cur.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+        if k > 0:
+            pose = ref.align(pose, cur, conf)
+            h2d.append(ref.last_h2d_bytes()[0])
+        ref.update(pose, cur)
+        out.append(np.array(pose))
+        cur.close()
+        cur = frames.Frame(trans=init, width=S, height=S, cell_side=float(S), calculate_cells_params=False)
+    return ref, np.array(out), h2d, z
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exact", [False, True])
+def test_callback_runs_on_the_device_mirror(monkeypatch, exact):
+    """loadLaser -> align -> update with the map resident in HBM: the reference's golden track, 4 bytes per beam over PCIe
+    (16 per point with NDTPSO_SHIM_EXACT_SCAN=1, which keeps the device map bit-identical to the host-built one)."""
+    ref, got, h2d, z = _callback_track(monkeypatch, exact)
+    want = z["track/poses"][:len(got)]
+    assert np.abs(got - want).max() <= 1e-4, (got, want)
+    assert ref.device_resident
+    P, I = 30, 20
+    stream = 4 * (3 + 3 * P + 6 * P * I)
+    beams = z["track/ranges"].shape[1]
+    for b in h2d:
+        if exact:
+            assert stream + 16 * 300 < b <= stream + 16 * beams + 64
+        else:
+            assert b <= stream + 4 * beams + 128, b  # the scan as ranges + the random numbers + guess: never the table
+    dev = ref.device_map_table()
+    host = ref.map_table()  # builds the host copy on demand
+    assert np.array_equal(dev["built"], host["built"])
+    m = host["built"].astype(bool)
+    if exact:
+        assert np.array_equal(dev["mean"][m], host["mean"][m]) and np.array_equal(dev["inv_cov"][m], host["inv_cov"][m])
+    else:  # the device redid loadLaser with its own sincos: points within a few ulp of the host's
+        assert np.allclose(dev["mean"][m], host["mean"][m], rtol=0, atol=1e-9)
+    ref.close()
+
+
+@pytest.mark.gpu
+def test_mirror_is_dropped_when_points_bypass_update(monkeypatch):
+    """A point added to the map directly (addPoint / loadLaser on the map itself) is not mirrored: the frame goes back to
+    uploading its table per align, and still gives the reference's answers."""
+    ref, got, _, z = _callback_track(monkeypatch, False, n_scans=4)
+    assert ref.device_resident
+    cfg, s = syn.CFG1, syn.CFG1.sensor
+    ref.load_laser(z["track/ranges"][4], s.angle_min, s.angle_increment, s.range_max)  # straight into the map
+    assert not ref.device_resident
+    cur = frames.Frame(width=cfg.map_size_m, height=cfg.map_size_m, cell_side=float(cfg.map_size_m), calculate_cells_params=False)
+    cur.load_laser(z["track/ranges"][5], s.angle_min, s.angle_increment, s.range_max)
+    pose = ref.align(got[-1], cur)
+    assert np.isfinite(pose).all() and ref.last_h2d_bytes()[0] == 0 and not ref.device_resident
+    ref.close()
+    cur.close()
+
+
+def test_frames_built_without_align_never_touch_the_device():
+    """Map building alone (what bench.py's workload generator does thousands of times) stays on the host: the mirror is only
+    created by the first align."""
+    ref, q = frames.frames_from_scans(syn.scene_a(syn.CFG1))
+    assert not ref.device_resident
+    assert ref.map_table()["built"].sum() > 0
+    ref.close()
+    q.close()

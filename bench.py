@@ -358,7 +358,9 @@ def run_tracking(B, conf, steps, device, groups=2):
     ctxs, dfs = [], []
     for lo, hi in bounds:
         c = capi.Context(device)
-        df = dframes.DeviceFrames(c, hi - lo, S, S, cfg.cell_side, s.beams, max_cells=1024, flags=dframes.DF_NO_CLUSTER if groups > 1 else 0)
+        # pools sized from what the scene needs (389 cells created, < 30 points per cell and scan), not for the worst case: 1024 cells per robot,
+        # rings of 256 points per cell (a ring only has to hold a cell's CURRENT slot); NDTPSO_DF_CELL_POOL_FULL / _WINDOW_TRUNCATED guard both
+        df = dframes.DeviceFrames(c, hi - lo, S, S, cfg.cell_side, s.beams, max_cells=1024, window_points=256, flags=dframes.DF_NO_CLUSTER if groups > 1 else 0)
         for k in range(5):  # the map: 5 scans per robot merged at their known poses
             df.load_laser(np.stack([ss.map_scans[k][1] for ss in sets[lo:hi]]), s.angle_min, s.angle_increment, s.range_max)
             df.update(np.array([ss.map_scans[k][0] for ss in sets[lo:hi]]))
@@ -399,6 +401,77 @@ def run_tracking(B, conf, steps, device, groups=2):
     for df, c in zip(dfs, ctxs):
         df.close()
         c.close()
+    return out
+
+
+def run_callback(steps, population, iterations):
+    """The reference's whole per-scan callback (src/ndtpso_slam_node.cpp:186-198: loadLaser -> align -> update) for ONE robot,
+    written against the drop-in NDTFrame (libndtpso_slam.so, what the ROS node links): the map stays in HBM (device mirror), the
+    scan crosses PCIe as 4 bytes per beam.  Beside it the unmodified reference's callback on this box: on one core and as shipped
+    (OpenMP team inside the match).  population/iterations None = the 2-argument align(), which always runs 30 x 50."""
+    import ctypes as C
+
+    from ndtpso_slam_b200 import capi, frames, synthetic as syn
+    cfg = syn.CFG2
+    s, S = cfg.sensor, cfg.map_size_m
+    room = syn.Room(S)
+    ss = syn.trajectory_problem(cfg, 0)
+    scans = [r for _, r in ss.map_scans] + [syn.make_scan(room, s, (ss.true_pose[0] + 0.02 * k, ss.true_pose[1] + 0.005 * k, ss.true_pose[2] + 0.001 * k),
+                                                          syn.NoiseLCG(4242 + k)) for k in range(steps)]
+    init = tuple(ss.map_scans[0][0])
+    conf = capi.PsoConfig.make(population=population, iterations=iterations) if population else None
+
+    def drive(make_map, make_scan_frame, align, update, close):
+        ref = make_map()
+        pose, ts = np.array(init), []
+        for k, ranges in enumerate(scans):
+            t0 = time.perf_counter()
+            cur = make_scan_frame(k == 0)
+            cur.load_laser(ranges, s.angle_min, s.angle_increment, s.range_max)
+            if k > 0:
+                pose = align(ref, pose, cur)
+            update(ref, pose, cur)
+            ts.append(time.perf_counter() - t0)
+            close(cur)
+        return ref, pose, ts
+
+    C.CDLL(None).srand(1)
+    ref, pose_gpu, ts = drive(lambda: frames.Frame(width=S, height=S, cell_side=cfg.cell_side, calculate_cells_params=True),
+                              lambda first: frames.Frame(trans=init, width=S, height=S, cell_side=cfg.cell_side if first else float(S), calculate_cells_params=False),
+                              lambda r, p, c: r.align(p, c, conf), lambda r, p, c: r.update(p, c), lambda c: c.close())
+    h2d = ref.last_h2d_bytes()
+    out = {"ms_per_scan": 1e3 * float(np.median(ts[len(ss.map_scans):])), "scans": steps, "swarm": f"{population or 30} x {iterations or 50}",
+           "device_resident_map": bool(ref.device_resident), "h2d_bytes_last_scan": {"align": h2d[0], "update": h2d[1]},
+           "api": "drop-in NDTFrame (libndtpso_slam.so): loadLaser + align + update per scan, one robot"}
+    ref.close()
+    try:
+        from oracle import binding
+        if os.path.exists(binding.REF_SO):
+            R = binding.Reference()
+            cores = len(os.sched_getaffinity(0))
+            for label, threads in (("reference_one_core", 1), ("reference_as_shipped_openmp", cores)):
+                R.lib.ref_omp_set_num_threads(threads)
+                R.srand(1)
+                if population:  # an explicit swarm: pso_optimization with the deviation rule of align (ndtframe.cpp:253) done here
+                    state = {"it": 0, "prev": np.zeros(3), "diff": np.zeros(3)}
+
+                    def align(r, p, c, state=state, threads=threads):
+                        dev = (0.1, 0.1, 3.1415e-3) if state["it"] < 2 else tuple(np.abs(2 * state["diff"]))
+                        state["it"] += 1
+                        po, _ = R.pso(r, c, p, dev, population, iterations, use_seed=False, num_threads=-1 if threads > 1 else 1)
+                        state["diff"], state["prev"] = po - state["prev"], po
+                        return po
+                else:
+                    def align(r, p, c):
+                        return R.align(r, p, c)
+                _, pose_ref, tr = drive(lambda: R.frame(width=S, height=S, cell_side=cfg.cell_side, init_windows=True),
+                                        lambda first: R.frame(trans=init, width=S, height=S, cell_side=cfg.cell_side if first else float(S), init_windows=False),
+                                        align, lambda r, p, c: r.update(p, c), lambda c: None)
+                out[label] = {"ms_per_scan": 1e3 * float(np.median(tr[len(ss.map_scans):])), "threads": threads}
+                if threads == 1:
+                    out["max_abs_dpose_vs_reference_one_core"] = float(np.abs(pose_gpu - pose_ref).max())
+    except Exception as e:  # the CPU legs are a comparison, not the measurement
+        out["reference_error"] = str(e)
     return out
 
 
@@ -657,6 +730,10 @@ def _run_gpu_arm(args, real_stdout):
     if rank == 0 and wl.name == "cfg2" and not args.no_tracking:
         tracking = run_tracking(B, conf, steps=max(4, min(args.steps, 12)), device=local, groups=args.tracking_groups)
 
+    callback = None
+    if rank == 0 and wl.name == "cfg2" and not args.no_tracking:
+        callback = {"align_default_30x50": run_callback(10, None, None), "swarm_70x50": run_callback(10, 70, 50)}
+
     rc = 0
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -721,6 +798,7 @@ def _run_gpu_arm(args, real_stdout):
                               "note": "one resident batch, one stream, L2 flushed (256 MiB write) between steps, per-step CUDA events"},
             "single_match": single,
             "tracking": tracking,
+            "callback": callback,
             "per_match": {"rounds": float(stats[:, 0].mean()), "gbest_updates": float(stats[:, 1].mean()), "fp64_evaluations": float(stats[:, 2].mean()),
                           "settled_by_fp32_screen": float(stats[:, 3].mean())},
             "pose0": [float(v) for v in pose[0]],

@@ -625,7 +625,12 @@ def _run_gpu_arm(args, real_stdout):
     launches = ctx.launch_count() - launches0
     total_ms = float(ev_start.elapsed_time(ev_end))
 
-    # sustained: the same loop for at least --sustain-seconds (not fewer steps than the timed region)
+    # sustained: the same loop for at least --sustain-seconds (not fewer steps than the timed region); every rank must run the
+    # same number of steps (the exchange waits for all of them), so the count comes from the slowest rank's timed region
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
     n_sus = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / max(total_ms / args.steps, 1e-3))))
     barrier()
     ev_s0, ev_s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -101,6 +101,12 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   b += 13 * Pn * (int)sizeof(double);
   return (b + 15) & ~15;
 }
+// The screen's records, n of them (null record included), in blocks of eight: [8 x {l00, l11, l10, kappa2}][8 x {-ox, -oy, -, -}].
+// Record r's first half sits at 256 (r / 8) + 16 (r % 8), its second half 128 bytes further: consecutive records — the
+// neighbouring cells a warp's points fall into — lie in different shared-memory banks (tools/microbench/lds_wavefronts.cu:
+// with whole records 32 bytes apart, records r and r + 4 collide).
+__host__ __device__ inline int screen_rec_bytes(int n) { return ((n + 7) / 8) * 256; }
+__host__ __device__ inline unsigned screen_rec_offset(unsigned r) { return 256u * (r >> 3) + 16u * (r & 7u); }
 // shared memory of the fp32 screen without its record table: pose32, lbpart, wsurv
 __host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
   return (P + 1) * 32 + round16((P + 1) * NW * 4) + round16(NW * (P + 2) * 2);
@@ -109,7 +115,7 @@ __host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
 // the largest record count of the batch, null record included) the fp32 records take screen_recs * 32 bytes more.
 __host__ __device__ inline int sliced_smem_bytes(int P, int PW, int WP, int table_bytes, int screen_recs = 0) {
   return kSlicedTableOffset + table_bytes + sliced_swarm_smem_bytes(P, PW, WP) +
-         (screen_recs > 0 ? sliced_screen_fixed_bytes(P, PW) + round16(screen_recs * 32) : 0);
+         (screen_recs > 0 ? sliced_screen_fixed_bytes(P, PW) + screen_rec_bytes(screen_recs) : 0);
 }
 
 // table_bytes = this CTA's staged table: [fp32 records (screen only)][grid][fp64 records].  Every pointer is `base` plus an
@@ -159,7 +165,7 @@ struct SliceCtx {
   double x_min, x_max, y_min, y_max, hw, hh, cs, inv_cs, hw_s, hh_s;
   double l2e, ln2hi, ln2lo, c7, c6, c5, c4, c3;  // fast_exp constants kept out of the immediate field
   int gw, base, span, null_id;
-  unsigned goff;  // screened launches: the grid holds goff + 32 * record id (the shared-memory address of the screen's record)
+  unsigned goff;  // screened launches: the grid holds goff + screen_rec_offset(record id), the shared-memory address of the screen's record
 };
 
 // One scan point against one candidate pose: subtracts exp(-(d' S d)/2) from acc iff the point is
@@ -195,7 +201,9 @@ __device__ __forceinline__ void slice_point(const SliceCtx& m, const double2 p, 
   const unsigned g = static_cast<unsigned>(ix + m.gw * iy - m.base);
   const bool in_strip = inb && (g < static_cast<unsigned>(m.span));
   const unsigned ge = m.grid[in_strip ? g : static_cast<unsigned>(m.span)];
-  const unsigned r = GSHIFT ? (ge - m.goff) >> GSHIFT : ge;  // screened launches keep goff + id * 32 in the grid
+  const unsigned ga = ge - m.goff;
+  // screened launches keep the shared address of the screen's record in the grid: goff + screen_rec_offset(id)
+  const unsigned r = GSHIFT ? ((ga >> 8) << 3) | ((ga >> 4) & 7u) : ge;
   const double* q = m.rec + 6 * r;
   // the sliced kernel only runs on symmetric tables (S01 == S10 bit for bit, which is what
   // NDTCell::s_calc_covar_inverse produces, ndtcell.cpp:109-110): 40 bytes per record instead of 48
@@ -356,9 +364,9 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       for results flushed to zero (ex2.approx.ftz below 2^-126; the fp64 side flushes too, which only raises its cost).
 // cost >= L because each fp64 term is >= -(upper bound of its exponential).
 struct ScreenCtx {
-  // shared: records [n_rec + 1][32 bytes] = {l00, l11, l10, kappa2, -ox, -oy, -, -} at the 32-bit shared address rec32
+  // shared: records {l00, l11, l10, kappa2}, {-ox, -oy, -, -} in blocks of eight (screen_rec_bytes) from the 32-bit shared address rec32
   unsigned rec32;
-  const unsigned short* grid;  // shared: the 32-bit shared ADDRESS of the cell's record (rec32 + 32 * record id; below 2^16)
+  const unsigned short* grid;  // shared: the 32-bit shared ADDRESS of the cell's record (rec32 + screen_rec_offset(id); below 2^16)
   float beta_c;                // 0.5 - beta
   int gw;
   unsigned span, nbase;        // nbase = -(first cell of the strip + the magic bits of both coordinates)
@@ -370,9 +378,9 @@ __device__ __forceinline__ float4 lds_f4(unsigned a) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
-__device__ __forceinline__ float2 lds_f2_16(unsigned a) {
+__device__ __forceinline__ float2 lds_f2_128(unsigned a) {
   float2 v;
-  asm("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  asm("ld.shared.v2.f32 {%0, %1}, [%2+128];" : "=f"(v.x), "=f"(v.y) : "r"(a));
   return v;
 }
 
@@ -400,8 +408,8 @@ struct ScreenPts {
 // One scan point against one candidate, with Blackwell's packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2: two IEEE results per
 // instruction) wherever the two coordinates go through the same operation: the upper bound of the point's exp(.).
 //   px2 = (px, px), py2 = (py, py);  tuv = (tu, tv), cs = (ck, sk), sc = (-sk, ck) of the candidate.
-// 21 instructions; three shared-memory loads (grid entry 2 bytes, record 16 + 8 bytes: 6.6 wavefronts measured), which is what
-// bounds the loop together with instruction issue (profiles/).
+// 21 instructions; three shared-memory loads (grid entry 2 bytes, record 16 + 8 bytes), which is what bounds the loop together
+// with instruction issue (profiles/).
 __device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 px2, const float2 py2, const float2 tuv, const float2 cs,
                                               const float2 sc) {
   const float2 uv = __ffma2_rn(px2, cs, __ffma2_rn(py2, sc, tuv));             // cell coordinates - 0.5
@@ -413,7 +421,7 @@ __device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 p
   const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y);
   const unsigned ra = m.grid[__viaddmin_u32(g, m.nbase, m.span)];
   const float4 l = lds_f4(ra);       // l00, l11, l10, kappa2
-  const float2 no = lds_f2_16(ra);   // -ox, -oy
+  const float2 no = lds_f2_128(ra);  // -ox, -oy
   const float2 d = __fadd2_rn(df, no);
   const float2 zz = __fmul2_rn(make_float2(l.x, l.y), d);                      // l00 d0, l11 d1
   const float z0 = fmaf(l.z, d.y, zz.x);
@@ -1102,7 +1110,7 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   const int span = nrows * mp.gw;
   const int rec_bytes = (n_rec + 1) * 48;
   const int grid_bytes = round16((span + 1) * 2);
-  const int rec32_bytes = screen ? (n_rec + 1) * 32 : 0;
+  const int rec32_bytes = screen ? screen_rec_bytes(n_rec + 1) : 0;
   const SlicedSmem sm = carve_sliced(smem_raw, P, tp.PW, tp.CL == 1 ? 0 : tp.NW, rec32_bytes + grid_bytes + rec_bytes, screen);
   unsigned char* s_rec32 = sm.table;
   unsigned short* s_grid = reinterpret_cast<unsigned short*>(sm.table + rec32_bytes);
@@ -1190,13 +1198,13 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
     const double cs2 = mp.cs * mp.cs;
     for (int g = tid; g <= span; g += T) {
       const int r = (g < span) ? s_grid[g] : n_rec;
-      s_grid[g] = static_cast<unsigned short>(rec32_addr + r * 32);
+      s_grid[g] = static_cast<unsigned short>(rec32_addr + screen_rec_offset(r));
       if (g < span && r == n_rec) continue;  // unbuilt cell: points at the null record
-      float* o = reinterpret_cast<float*>(s_rec32 + 32 * r);
+      float* o = reinterpret_cast<float*>(s_rec32 + screen_rec_offset(r));  // o[0..3] = first half, o[32..35] = second half (128 bytes on)
       if (r == n_rec) {  // the null record
         o[0] = o[1] = o[2] = 0.f;
         o[3] = -1e30f;
-        o[4] = o[5] = o[6] = o[7] = 0.f;
+        o[32] = o[33] = o[34] = o[35] = 0.f;
         continue;
       }
       const double* q = rec + 6 * r;
@@ -1223,9 +1231,9 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
       o[1] = static_cast<float>(l11 * scale);
       o[2] = static_cast<float>(l10 * scale);
       o[3] = __double2float_ru(kappa * 1.4426950408889634);
-      o[4] = static_cast<float>(-ox);
-      o[5] = static_cast<float>(-oy);
-      o[6] = o[7] = 0.f;
+      o[32] = static_cast<float>(-ox);
+      o[33] = static_cast<float>(-oy);
+      o[34] = o[35] = 0.f;
     }
     sc->rec32 = rec32_addr;
     sc->grid = s_grid;
@@ -1252,9 +1260,9 @@ __device__ __forceinline__ Topo make_topo(int groups) {
 }
 
 // the screen's records start at a fixed offset of the dynamic shared memory and are addressed by 16-bit shared addresses
-constexpr int kScreenMaxRecords = 1980;  // null record included: 1024 (room for the window's base) + kSlicedTableOffset + 1980 * 32 < 2^16
+constexpr int kScreenMaxRecords = 1976;  // null record included: 1024 (room for the window's base) + kSlicedTableOffset + screen_rec_bytes(1976) < 2^16
 __device__ __forceinline__ bool sliced_screen_fits(const unsigned char* smem_raw, int n_rec) {
-  return smem_u32(smem_raw) + kSlicedTableOffset + 32u * static_cast<unsigned>(n_rec + 1) <= 65536u;
+  return smem_u32(smem_raw) + kSlicedTableOffset + static_cast<unsigned>(screen_rec_bytes(n_rec + 1)) <= 65536u;
 }
 
 // Host guarantees: every table is compact and symmetric and fits the dynamic shared memory;

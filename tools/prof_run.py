@@ -6,6 +6,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ndtpso_slam_b200 import capi, workload  # noqa: E402
 
+if os.environ.get("NDTPSO_PROF_LIB"):  # a variant built by tools/variant_time.py
+    capi._build.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "lib_" + os.environ["NDTPSO_PROF_LIB"] + ".so")
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 solves = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ctx = capi.Context(0)

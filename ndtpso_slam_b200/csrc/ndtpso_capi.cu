@@ -687,7 +687,8 @@ int launch_pso(ndtpso_batch* bt, int smem) {
 //         2^-24 (12 pmax' + 3.01 W)/cs + 2^-23 with pmax' = max(pmax, 1), which covers every higher-order term and the fp64
 //         side's own rounding as long as (pmax + W)/cs <= 2^22 (checked here).  pmax, W, 1/cs: the largest of the batch.
 //   beta: band around cell edges inside which fp32 and fp64 may pick different cells; it only has to be >= du, and is taken
-//         four times that, at least 5e-4.
+//         twice that.  (A lane of the screen that has ANY point in the band counts all its points as worst case, so the band's
+//         width costs tightness: at 2 du about 0.2 % of a typical cost.)
 bool screen_params(const ndtpso_batch* bt, PsoParams* prm, bool ignore_option = false) {
   prm->screen = 0;
   const ndtpso_ctx* ctx = bt->ctx;
@@ -697,7 +698,7 @@ bool screen_params(const ndtpso_batch* bt, PsoParams* prm, bool ignore_option = 
   const double pmax = std::max(bt->scr_pmax, 1.0), W = 2. * bt->scr_ext;
   if ((pmax + W) * bt->scr_inv_cs > 4194304.) return false;
   const double du = u24 * (12. * pmax + 3.01 * W) * bt->scr_inv_cs + 2. * u24;
-  const double beta = std::max(5e-4, 4. * du);
+  const double beta = 2. * du;
   if (beta > 0.05) return false;
   prm->screen = 1;
   prm->scr_du = (float)(du * 1.000001);  // rounded to fp32: 1e-6 relative covers the rounding
@@ -792,6 +793,12 @@ int try_cluster(ndtpso_batch* bt, bool forced) {
 #endif
 }
 
+#ifndef NDTPSO_NPT4_T
+#define NDTPSO_NPT4_T 320  // __launch_bounds__ of the 4-points-per-thread shape: threads, CTAs per SM
+#endif
+#ifndef NDTPSO_NPT4_MINB
+#define NDTPSO_NPT4_MINB 2
+#endif
 #ifndef NDTPSO_MINB3
 #define NDTPSO_MINB3 2  // CTAs per SM the 3-points-per-thread shape is compiled for (2 => 80 registers); tools/variant_time.py
 #endif
@@ -866,7 +873,7 @@ int launch_sliced(ndtpso_batch* bt) {
   if (smem > ctx->max_smem_optin) return 1;
   const int jb = ctx->opt_cand_batch;
 #ifdef NDTPSO_DEV_FAST
-  return npt == 3 ? launch_sliced_cfg<3, 4, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr) : npt == 4 ? launch_sliced_cfg<4, 4, 1, 320, 2>(bt, nw, 1, smem, scr) : 1;
+  return npt == 3 ? launch_sliced_cfg<3, 4, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr) : npt == 4 ? launch_sliced_cfg<4, 4, 1, NDTPSO_NPT4_T, NDTPSO_NPT4_MINB>(bt, nw, 1, smem, scr) : 1;
 #else
   switch (npt) {
     case 1: return jb == 1 ? launch_sliced_cfg<1, 1, 1, 640, 1>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<1, 2, 1, 640, 1>(bt, nw, 1, smem, scr)
@@ -875,7 +882,7 @@ int launch_sliced(ndtpso_batch* bt) {
                                                                                         : launch_sliced_cfg<2, 4, 1, 640, 1>(bt, nw, 1, smem, scr);
     case 3: return jb == 1 ? launch_sliced_cfg<3, 1, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr) : jb == 2 ? launch_sliced_cfg<3, 2, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr)
                                                                                         : launch_sliced_cfg<3, 4, 1, 384, NDTPSO_MINB3>(bt, nw, 1, smem, scr);
-    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, 320, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<4, 2, 1, 320, 2>(bt, nw, 1, smem, scr);
+    case 4: return jb == 1 ? launch_sliced_cfg<4, 1, 1, NDTPSO_NPT4_T, NDTPSO_NPT4_MINB>(bt, nw, 1, smem, scr) : launch_sliced_cfg<4, 2, 1, NDTPSO_NPT4_T, NDTPSO_NPT4_MINB>(bt, nw, 1, smem, scr);
     case 5: return jb == 1 ? launch_sliced_cfg<5, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<5, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
     default: return jb == 1 ? launch_sliced_cfg<6, 1, 1, 256, 2>(bt, nw, 1, smem, scr) : launch_sliced_cfg<6, 2, 1, 256, 2>(bt, nw, 1, smem, scr);
   }

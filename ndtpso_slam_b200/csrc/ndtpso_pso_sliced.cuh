@@ -83,7 +83,7 @@ struct SlicedSmem {
   double* pb;       // [P][3]
   double* pbc;      // [P]
   // fp32 screening (CL == 1 only; null when off)
-  float4* pose32;   // [P+1][2] {tu, tv, c/cs, s/cs}, {-s/cs, c/cs, 0, 0} of the current round's candidates: the register pairs the packed transform takes
+  float4* pose32;   // [P+1] {tu, tv, c/cs, s/cs} of the current round's candidates (cell units)
   float* lbpart;    // [(P+1)*NW] per-warp partial sums of the upper bounds
   unsigned short* wsurv;  // [NW][P+2] per warp: the candidates that need the fp64 evaluation, ascending
 };
@@ -101,15 +101,18 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   b += 13 * Pn * (int)sizeof(double);
   return (b + 15) & ~15;
 }
-// The screen's records, n of them (null record included), in blocks of eight: [8 x {l00, l11, l10, kappa2}][8 x {-ox, -oy, -, -}].
-// Record r's first half sits at 256 (r / 8) + 16 (r % 8), its second half 128 bytes further: consecutive records — the
+// The screen's records, n of them (null record included), in blocks of eight: [8 x {l00, l11, -ox, -oy}][8 x {l10, -, -, -}].
+// Record r's first part sits at 256 (r / 8) + 16 (r % 8), its second part 128 bytes further: consecutive records — the
 // neighbouring cells a warp's points fall into — lie in different shared-memory banks (tools/microbench/lds_wavefronts.cu:
-// with whole records 32 bytes apart, records r and r + 4 collide).
+// with whole records 32 bytes apart, records r and r + 4 collide).  20 bytes are loaded per evaluation (LDS.128 + LDS.32): the
+// loop is bound by shared-memory wavefronts, which a warp-wide load costs in proportion to its width (3.1 / 1.7 / 1.0 for
+// 16 / 8 / 4 bytes with the ~6 records a warp's 32 beams hit), so the additive term of the exponent is ONE value for the
+// whole table (ScreenCtx::kappa2) instead of a sixth field of every record.
 __host__ __device__ inline int screen_rec_bytes(int n) { return ((n + 7) / 8) * 256; }
 __host__ __device__ inline unsigned screen_rec_offset(unsigned r) { return 256u * (r >> 3) + 16u * (r & 7u); }
 // shared memory of the fp32 screen without its record table: pose32, lbpart, wsurv
 __host__ __device__ inline int sliced_screen_fixed_bytes(int P, int NW) {
-  return (P + 1) * 32 + round16((P + 1) * NW * 4) + round16(NW * (P + 2) * 2);
+  return (P + 1) * 16 + round16((P + 1) * NW * 4) + round16(NW * (P + 2) * 2);
 }
 // total dynamic shared memory: table_bytes = (n_rec + 1) * 48 + round16((span + 1) * 2).  With the screen (screen_recs > 0:
 // the largest record count of the batch, null record included) the fp32 records take screen_recs * 32 bytes more.
@@ -149,7 +152,7 @@ __device__ __forceinline__ SlicedSmem carve_sliced(unsigned char* base, int P, i
   s.wsurv = nullptr;
   if (screen) {
     s.pose32 = reinterpret_cast<float4*>(base + o);
-    o += (P + 1) * 32;
+    o += (P + 1) * 16;
     s.lbpart = reinterpret_cast<float*>(base + o);
     o += round16((P + 1) * PW * 4);
     s.wsurv = reinterpret_cast<unsigned short*>(base + o);
@@ -351,12 +354,21 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       and again z_k^2 >= (1 - t) z~_k^2/S - (1/t - 1) ez_k^2 (also when |z~_k| < sqrt(S) ez_k: the right side is then <= 0).
 //       xe = fl(-z~1^2 + fl(-z~0^2 + kappa2)) >= kappa2 (1 - 2u') - (z~0^2 + z~1^2)(1 + 2u'), u' = u(1 + u) (the squares
 //       are exact inside the FMAs).  With S = (1 - t)^2 (1 - 2^-22) log2(e) and
-//           kappa2 >= 1.000001 log2(e) [(ez_0^2 + ez_1^2) + hs delta^2]/t        (rounded up)
-//       the chain gives  xe >= -A(d*) log2(e), i.e.  e = ex2(min(xe, 0)) >= exp(-A(d*)).   t is chosen per record: sqrt of
-//       the absolute terms, clamped to [2^-10, 2^-3], which balances the relative loosening t A against the absolute one.
+//           kappa2 (1 - 2^-22) >= 1.000001 log2(e) [(ez_0^2 + ez_1^2) + hs delta^2]/t
+//       the chain gives  xe >= -A(d*) log2(e), i.e.  e = ex2(xe) >= exp(-A(d*))  (xe may exceed 0 by at most kappa2: e is then
+//       a little above 1, still an upper bound).  kappa2 is ONE fp32 value for the whole table (kept in a register; a record
+//       is 20 bytes instead of 24) and t is what each record needs to get by with it:
+//           kappa0_r = (ez_0^2 + ez_1^2) + hs delta^2,    t_r = 1.000001 log2(e) kappa0_r / (kappa2 (1 - 2^-22)),
+//           kappa2 = log2(e) sqrt(mean_r kappa0_r):
+//       the additive loosening 0.69 kappa2 of every term against the relative loosening t_r A of the exponents, balanced for
+//       A = 1, the mean exponent of a two-dimensional Gaussian's mass (screen_kappa2 below; two passes over the records in
+//       the prologue, fixed-order reductions).  A record that would need t_r > 1/2 (a needle far sharper than the rest of its
+//       table) gets the trivial bound instead: a zero factor, z = 0, e = 2^kappa2 >= 1 for every point of its cell — so one
+//       degenerate cell costs its own points' terms, not the tightness of the whole table.
 //       The Cholesky factor is computed in fp64 and shrunk by what its own rounding could add (1e-12 relative on l00, l10;
 //       4e-15 H11 absolute on l11^2 before the root, which also covers cancellation in H11 - l10^2).
-//       The null record (unbuilt cell, outside the strip) has kappa2 = -1e30: e = 0 without a test.
+//       The null record (unbuilt cell, outside the strip) is {l00 = 1, l11 = 0, -ox = 1e18, -oy = 0, l10 = 0}: z0 = 1e18,
+//       xe = kappa2 - 1e36, e = 0 without a test.
 //   (5) Sum.  ex2.approx is within 2 ulp (2^-22); the per-lane accumulation (NPT multiply-adds with weights 0 or 1), the warp tree (5) and the sum over
 //       the warps (NW - 1) are fp32 additions of non-negative terms: relative error <= (NPT + NW + 4) u < 2^-19 for every
 //       shape launched.  The fp64 evaluation's own deviation from exact arithmetic (FMA roundings in the exponent, ~1e-12
@@ -364,10 +376,11 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       for results flushed to zero (ex2.approx.ftz below 2^-126; the fp64 side flushes too, which only raises its cost).
 // cost >= L because each fp64 term is >= -(upper bound of its exponential).
 struct ScreenCtx {
-  // shared: records {l00, l11, l10, kappa2}, {-ox, -oy, -, -} in blocks of eight (screen_rec_bytes) from the 32-bit shared address rec32
+  // shared: records {l00, l11, -ox, -oy}, {l10, -, -, -} in blocks of eight (screen_rec_bytes) from the 32-bit shared address rec32
   unsigned rec32;
   const unsigned short* grid;  // shared: the 32-bit shared ADDRESS of the cell's record (rec32 + screen_rec_offset(id); below 2^16)
   float beta_c;                // 0.5 - beta
+  float kappa2;                // the exponent's additive term, one value for the table (derivation (4))
   int gw;
   unsigned span, nbase;        // nbase = -(first cell of the strip + the magic bits of both coordinates)
 };
@@ -378,9 +391,9 @@ __device__ __forceinline__ float4 lds_f4(unsigned a) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
-__device__ __forceinline__ float2 lds_f2_128(unsigned a) {
-  float2 v;
-  asm("ld.shared.v2.f32 {%0, %1}, [%2+128];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+__device__ __forceinline__ float lds_f1_128(unsigned a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+128];" : "=f"(v) : "r"(a));
   return v;
 }
 
@@ -391,11 +404,10 @@ constexpr int kScreenMagicBits = 0x4B400000;     // its bit pattern
 __device__ __forceinline__ void store_pose32(float4* pose32, int j, double x, double y, double c, double s, double inv_cs, double off_u,
                                              double off_v) {
   const float ck = static_cast<float>(c * inv_cs), sk = static_cast<float>(s * inv_cs);  // c/cs is exact in fp64: one rounding
-  pose32[2 * j] = make_float4(static_cast<float>(fma(x, inv_cs, off_u)), static_cast<float>(fma(y, inv_cs, off_v)), ck, sk);
-  pose32[2 * j + 1] = make_float4(-sk, ck, 0.f, 0.f);
+  pose32[j] = make_float4(static_cast<float>(fma(x, inv_cs, off_u)), static_cast<float>(fma(y, inv_cs, off_v)), ck, sk);
 }
 
-// This lane's scan points for the screen: the (x, x), (y, y) pairs of the packed transform, and per slot a weight (1 for a
+// This lane's scan points for the screen: the (x, y), (-y, x) pairs of the packed transform, and per slot a weight (1 for a
 // scan point, 0 for padding).  A padding slot holds a COPY of one of the lane's own scan points (of the scan's first point in
 // a lane that has none), so it goes through the arithmetic like any point, cannot add a new "near a cell edge" case, and is
 // dropped from the sum by its weight.
@@ -403,15 +415,18 @@ template <int NPT>
 struct ScreenPts {
   float2 px2[NPT], py2[NPT];
   float w[NPT];
+  float wsum;  // number of scan points this lane holds
 };
 
 // One scan point against one candidate, with Blackwell's packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2: two IEEE results per
-// instruction) wherever the two coordinates go through the same operation: the upper bound of the point's exp(.).
-//   px2 = (px, px), py2 = (py, py);  tuv = (tu, tv), cs = (ck, sk), sc = (-sk, ck) of the candidate.
-// 21 instructions; three shared-memory loads (grid entry 2 bytes, record 16 + 8 bytes), which is what bounds the loop together
-// with instruction issue (profiles/).
+// instruction) wherever the two coordinates go through the same operation: the upper bound of the point's exp(.) for a point
+// that is not within beta of a cell edge; `edge` collects max(|df.x|, |df.y|) over the points of a lane so that the caller
+// can test all of them at once (a 3-input FMNMX per point instead of compare + select).
+//   px2 = (px, py), py2 = (-py, px);  tuv = (tu, tv), cs = (ck, ck), sc = (sk, sk) of the candidate (scalar operands of the
+//   packed instructions): (u, v) = ck (px, py) + sk (-py, px) + (tu, tv).
+// Three shared-memory loads: grid entry (2 bytes), record (16 + 4 bytes).
 __device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 px2, const float2 py2, const float2 tuv, const float2 cs,
-                                              const float2 sc) {
+                                              const float2 sc, float& edge) {
   const float2 uv = __ffma2_rn(px2, cs, __ffma2_rn(py2, sc, tuv));             // cell coordinates - 0.5
   const float2 t2 = __fadd2_rn(uv, make_float2(kScreenMagic, kScreenMagic));   // round to nearest = floor of the cell coordinate, |uv| < 2^22
   const float2 fl = __fadd2_rn(t2, make_float2(-kScreenMagic, -kScreenMagic));
@@ -420,15 +435,16 @@ __device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 p
   // min(g + nbase, span) is one VIADDMNMX
   const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y);
   const unsigned ra = m.grid[__viaddmin_u32(g, m.nbase, m.span)];
-  const float4 l = lds_f4(ra);       // l00, l11, l10, kappa2
-  const float2 no = lds_f2_128(ra);  // -ox, -oy
-  const float2 d = __fadd2_rn(df, no);
+  const float4 l = lds_f4(ra);        // l00, l11, -ox, -oy
+  const float l10 = lds_f1_128(ra);
+  const float2 d = __fadd2_rn(df, make_float2(l.z, l.w));
   const float2 zz = __fmul2_rn(make_float2(l.x, l.y), d);                      // l00 d0, l11 d1
-  const float z0 = fmaf(l.z, d.y, zz.x);
-  const float xe = fmaf(-zz.y, zz.y, fmaf(-z0, z0, l.w));
+  const float z0 = fmaf(l10, d.y, zz.x);
+  const float xe = fmaf(-zz.y, zz.y, fmaf(-z0, z0, m.kappa2));
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(xe, 0.f)));          // 2 ulp, results below 2^-126 flushed: covered by the total's slack
-  return fmaxf(fabsf(df.x), fabsf(df.y)) > m.beta_c ? 1.f : e;                 // within beta of a cell edge: the worst case
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xe));                       // 2 ulp, results below 2^-126 flushed: covered by the total's slack
+  edge = fmaxf(fmaxf(edge, fabsf(df.x)), fabsf(df.y));
+  return e;
 }
 
 // warp sums of JB per-lane accumulators, packed like packed_warp_sum (same slot assignment)
@@ -487,22 +503,26 @@ __device__ __forceinline__ float packed_warp_sum_f<8>(const float (&a)[8], int l
 }
 
 // screen of candidates j .. j+JB-1 (clamped to hi-1) on this warp's slice: lbpart[j*NW + warp] = sum of the upper bounds
-template <int NPT, int JB>
+// (FULL: all JB candidates exist, j + JB <= hi: no clamping of the pose index, no test before the store)
+template <int NPT, int JB, bool FULL>
 __device__ __forceinline__ void screen_batch(const ScreenCtx& m, const ScreenPts<NPT>& p, const float4* pose32, float* lbpart, int j, int hi,
                                              int NW, int warp, int lane) {
   float acc[JB];
 #pragma unroll
   for (int b = 0; b < JB; ++b) {
-    const float4* q = pose32 + 2 * min(j + b, hi - 1);
-    const float4 ps = q[0];
-    const float2 tuv = make_float2(ps.x, ps.y), cs = make_float2(ps.z, ps.w), sc = *reinterpret_cast<const float2*>(q + 1);
-    acc[b] = screen_point(m, p.px2[0], p.py2[0], tuv, cs, sc) * p.w[0];  // the weight drops padding slots (copies of a scan point)
+    const float4 ps = pose32[FULL ? j + b : min(j + b, hi - 1)];
+    const float2 tuv = make_float2(ps.x, ps.y), cs = make_float2(ps.z, ps.z), sc = make_float2(ps.w, ps.w);
+    float edge = 0.f;
+    acc[b] = screen_point(m, p.px2[0], p.py2[0], tuv, cs, sc, edge) * p.w[0];  // the weight drops padding slots (copies of a scan point)
 #pragma unroll
-    for (int k = 1; k < NPT; ++k) acc[b] = fmaf(screen_point(m, p.px2[k], p.py2[k], tuv, cs, sc), p.w[k], acc[b]);
+    for (int k = 1; k < NPT; ++k) acc[b] = fmaf(screen_point(m, p.px2[k], p.py2[k], tuv, cs, sc, edge), p.w[k], acc[b]);
+    // a point within beta of a cell edge counts as the worst case, exp(.) = 1: if any of this lane's points is, all of them do
+    // (each term is <= 1 and the terms already added are >= 0, so adding the lane's point count keeps an upper bound)
+    acc[b] += edge > m.beta_c ? p.wsum : 0.f;
   }
   const float tot = packed_warp_sum_f<JB>(acc, lane);
   const int jj = j + packed_slot<JB>(lane);
-  if (packed_writer<JB>(lane) && jj < hi) lbpart[jj * NW + warp] = tot;
+  if (packed_writer<JB>(lane) && (FULL || jj < hi)) lbpart[jj * NW + warp] = tot;
 }
 
 // the screen over candidates [lo, hi): NDTPSO_SCREEN_JB at a time, then the rest in pairs
@@ -510,11 +530,11 @@ template <int NPT>
 __device__ __forceinline__ void screen_candidates(const ScreenCtx& m, const ScreenPts<NPT>& p, const float4* pose32, float* lbpart, int lo, int hi,
                                                   int NW, int warp, int lane) {
   int j = lo;
-  for (; j + NDTPSO_SCREEN_JB <= hi; j += NDTPSO_SCREEN_JB) screen_batch<NPT, NDTPSO_SCREEN_JB>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+  for (; j + NDTPSO_SCREEN_JB <= hi; j += NDTPSO_SCREEN_JB) screen_batch<NPT, NDTPSO_SCREEN_JB, true>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
 #if NDTPSO_SCREEN_JB > 4
-  for (; j + 4 <= hi; j += 4) screen_batch<NPT, 4>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+  for (; j + 4 <= hi; j += 4) screen_batch<NPT, 4, true>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
 #endif
-  for (; j < hi; j += 2) screen_batch<NPT, 2>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+  for (; j < hi; j += 2) screen_batch<NPT, 2, false>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
 }
 
 // this lane's fp32 copies of its scan points (pt[k] = point k*T + tid of the scan, padding = (1e200, 0)); `first` = the scan's
@@ -528,10 +548,13 @@ __device__ __forceinline__ void screen_points(const double2 (&pt)[NPT], const do
     const bool pad = pt[k].x > 1e199;
     const double2 q = pad ? own : pt[k];
     const float fx = static_cast<float>(q.x), fy = static_cast<float>(q.y);
-    p.px2[k] = make_float2(fx, fx);
-    p.py2[k] = make_float2(fy, fy);
+    p.px2[k] = make_float2(fx, fy);
+    p.py2[k] = make_float2(-fy, fx);
     p.w[k] = pad ? 0.f : 1.f;
   }
+  p.wsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) p.wsum += p.w[k];
 }
 
 // fp64 evaluation of the candidates listed in surv[i .. i+JB-1] (clamped to the last entry)
@@ -1097,6 +1120,41 @@ __device__ __forceinline__ void sliced_body_screened(const ScreenCtx& sc, const 
   }
 }
 
+// What the screen's record of one built cell is made of (derivation (3), (4) above "struct ScreenCtx"), in fp64:
+// q = the cell's fp64 record {mu_x, mu_y, -S00/2, -S01/2, -S10/2, -S11/2}, cell = its flat index, du = the coordinate error bound.
+struct ScreenRec {
+  double l00, l10, l11;  // Cholesky factor of H = (Sigma^-1 / 2) cs^2, shrunk by its own rounding
+  double ox, oy;         // the mean's offset from the cell's centre, in cell sides
+  double kappa0;         // (ez_0^2 + ez_1^2) + hs delta^2: the absolute terms of the exponent's bound, before the division by t
+};
+__device__ __forceinline__ ScreenRec screen_record(const double* q, int cell, const DevMap& mp, double du) {
+  ScreenRec r;
+  const double u24 = 5.9604644775390625e-08;
+  const double cs2 = mp.cs * mp.cs;
+  const double H00 = -q[2] * cs2, H01 = -q[3] * cs2, H11 = -q[5] * cs2;  // (Sigma^-1/2) in cell units
+  r.ox = (q[0] + mp.hw) * mp.inv_cs - ((cell % mp.gw) + 0.5);
+  r.oy = (q[1] + mp.hh) * mp.inv_cs - ((cell / mp.gw) + 0.5);
+  const double dl0 = du + u24 * (2. * fabs(r.ox) + 0.51), dl1 = du + u24 * (2. * fabs(r.oy) + 0.51), dl = fmax(dl0, dl1);
+  const double dm0 = fmax(fabs(-0.5 - r.ox), fabs(0.5 - r.ox)) + dl0, dm1 = fmax(fabs(-0.5 - r.oy), fabs(0.5 - r.oy)) + dl1;
+  const double sh = 1. - 1e-12;
+  r.l00 = H00 > 0. ? sqrt(H00) * sh : 0.;
+  r.l10 = r.l00 > 0. ? H01 / r.l00 * sh : 0.;
+  r.l11 = sqrt(fmax(H11 - r.l10 * r.l10 - 4e-15 * H11, 0.)) * sh;
+  const double ez0 = 4. * u24 * (r.l00 * dm0 + fabs(r.l10) * dm1), ez1 = 4. * u24 * r.l11 * dm1;
+  const double hs = H00 + 2. * fabs(H01) + H11;
+  r.kappa0 = ez0 * ez0 + ez1 * ez1 + hs * dl * dl;
+  return r;
+}
+// The table's kappa2 from the sum of its records' kappa0 (derivation (4)), rounded up to fp32; any positive finite value is
+// valid (the records adapt their t to it), this one balances the two loosenings.
+__device__ __forceinline__ float screen_kappa2(double k0sum, int n_rec) {
+  const double mean = n_rec > 0 ? k0sum / n_rec : 0.;
+  double k = 1.4426950408889634 * sqrt(mean);
+  if (!(k >= 9.5367431640625e-07)) k = 9.5367431640625e-07;  // never below 2^-20 (and not NaN)
+  if (!(k <= 0.25)) k = 0.25;                                  // a table of needles: most records then take the trivial bound
+  return __double2float_ru(k * 1.000001);
+}
+
 // Prologue shared by the production kernel and the phase-B microbenchmark: stages the compact
 // table with two bulk TMA copies, loads this thread's scan points into registers meanwhile
 // (coalesced 16-byte loads), and fills the loop-invariant context.
@@ -1188,53 +1246,57 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
   mbar_wait(sm.bar, 0);
   if (screen) {
     // fp32 records of the screen (derivation above "struct ScreenCtx"): one per built cell, found through the grid so that the
-    // cell is known; the grid entry is then replaced by the record's byte offset.  Every thread owns whole grid entries, and
+    // cell is known; the grid entry is then replaced by the record's shared address.  Every thread owns whole grid entries, and
     // the body has a __syncthreads before anyone else reads them.
     const double* rec = reinterpret_cast<const double*>(s_rec);
     const unsigned rec32_addr = smem_u32(s_rec32);  // sliced_screen_fits() made sure every record's address is below 2^16
     m.goff = rec32_addr;
     const double du = static_cast<double>(prm->scr_du);
-    const double u24 = 5.9604644775390625e-08;
-    const double cs2 = mp.cs * mp.cs;
+    const int cell0 = row0 * mp.gw;
+    // pass 1: what every record needs of the exponent's additive term (kappa0_r), its maximum and its mean -> kappa2
+    double k0sum = 0.;
+    for (int g = tid; g < span; g += T) {
+      const int r = s_grid[g];
+      if (r == n_rec) continue;
+      const double k0 = screen_record(rec + 6 * r, g + cell0, mp, du).kappa0;
+      k0sum += k0 < 1e300 ? k0 : 1e300;  // a non-finite kappa0 (its record takes the trivial bound) must not poison the mean
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) k0sum += __shfl_xor_sync(0xffffffffu, k0sum, off);  // fixed trees: the same kappa2 in every run
+    double* red = sm.partial;  // NW doubles: the swarm arrays are free until the body starts
+    if ((tid & 31) == 0) red[tid >> 5] = k0sum;
+    __syncthreads();
+    k0sum = 0.;
+    for (int w = 0; w < tp.NW; ++w) k0sum += red[w];
+    __syncthreads();  // `red` is read before anything else may write sm.partial
+    const float kappa2 = screen_kappa2(k0sum, n_rec);
+    const double kd = static_cast<double>(kappa2) * (1. - 2.384185791015625e-07);
+    // pass 2: the records
     for (int g = tid; g <= span; g += T) {
       const int r = (g < span) ? s_grid[g] : n_rec;
       s_grid[g] = static_cast<unsigned short>(rec32_addr + screen_rec_offset(r));
       if (g < span && r == n_rec) continue;  // unbuilt cell: points at the null record
-      float* o = reinterpret_cast<float*>(s_rec32 + screen_rec_offset(r));  // o[0..3] = first half, o[32..35] = second half (128 bytes on)
-      if (r == n_rec) {  // the null record
-        o[0] = o[1] = o[2] = 0.f;
-        o[3] = -1e30f;
-        o[32] = o[33] = o[34] = o[35] = 0.f;
+      float* o = reinterpret_cast<float*>(s_rec32 + screen_rec_offset(r));  // o[0..3] = first part, o[32] = second part (128 bytes on)
+      if (r == n_rec) {  // the null record: z0 = 1e18 whatever the point
+        o[0] = 1.f;
+        o[1] = 0.f;
+        o[2] = 1e18f;
+        o[3] = 0.f;
+        o[32] = 0.f;
         continue;
       }
-      const double* q = rec + 6 * r;
-      const double H00 = -q[2] * cs2, H01 = -q[3] * cs2, H11 = -q[5] * cs2;  // (Sigma^-1/2) in cell units
-      const int cell = g + row0 * mp.gw;
-      // the mean's offset from the cell's centre, in cell units
-      const double ox = (q[0] + mp.hw) * mp.inv_cs - ((cell % mp.gw) + 0.5), oy = (q[1] + mp.hh) * mp.inv_cs - ((cell / mp.gw) + 0.5);
-      const double dl0 = du + u24 * (2. * fabs(ox) + 0.51), dl1 = du + u24 * (2. * fabs(oy) + 0.51), dl = fmax(dl0, dl1);
-      const double dm0 = fmax(fabs(-0.5 - ox), fabs(0.5 - ox)) + dl0, dm1 = fmax(fabs(-0.5 - oy), fabs(0.5 - oy)) + dl1;
-      // Cholesky factor, shrunk by what its own rounding could add
-      const double sh = 1. - 1e-12;
-      const double l00 = H00 > 0. ? sqrt(H00) * sh : 0.;
-      const double l10 = l00 > 0. ? H01 / l00 * sh : 0.;
-      const double l11 = sqrt(fmax(H11 - l10 * l10 - 4e-15 * H11, 0.)) * sh;
-      const double ez0 = 4. * u24 * (l00 * dm0 + fabs(l10) * dm1), ez1 = 4. * u24 * l11 * dm1;
-      const double hs = H00 + 2. * fabs(H01) + H11;
-      // t trades the relative loosening t*A against the absolute one kappa0/t: balanced for A of order one
-      const double kappa0 = ez0 * ez0 + ez1 * ez1 + hs * dl * dl;
-      const double t = fmin(fmax(sqrt(kappa0), 0x1p-10), 0x1p-3);
-      const double scale = sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634) * (1. - 1e-12);
-      const double kappa = kappa0 / t * 1.000001;  // and the rounding of the sum it enters
+      const ScreenRec sr = screen_record(rec + 6 * r, g + cell0, mp, du);
+      const double t = 1.000001 * 1.4426950408889634 * sr.kappa0 / kd;
+      // !(t <= 1/2): this record needs more than the table's kappa2 gives (or is not finite): the trivial bound, e = 2^kappa2
+      const double scale = (t <= 0.5) ? sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634) * (1. - 1e-12) : 0.;
       // the factor's entries are rounded to fp32 here; that rounding is the first of the three ez counts per product
-      o[0] = static_cast<float>(l00 * scale);
-      o[1] = static_cast<float>(l11 * scale);
-      o[2] = static_cast<float>(l10 * scale);
-      o[3] = __double2float_ru(kappa * 1.4426950408889634);
-      o[32] = static_cast<float>(-ox);
-      o[33] = static_cast<float>(-oy);
-      o[34] = o[35] = 0.f;
+      o[0] = scale > 0. ? static_cast<float>(sr.l00 * scale) : 0.f;
+      o[1] = scale > 0. ? static_cast<float>(sr.l11 * scale) : 0.f;
+      o[2] = scale > 0. ? static_cast<float>(-sr.ox) : 0.f;
+      o[3] = scale > 0. ? static_cast<float>(-sr.oy) : 0.f;
+      o[32] = scale > 0. ? static_cast<float>(sr.l10 * scale) : 0.f;
     }
+    sc->kappa2 = kappa2;
     sc->rec32 = rec32_addr;
     sc->grid = s_grid;
     sc->beta_c = prm->scr_beta_c;

@@ -40,6 +40,8 @@ if name != "prod":
     capi._build.LIB_PATH = os.path.join(BUILD, f"lib_{name}.so")
 ctx = capi.Context(0)
 ctx.set_option(capi.OPT_CLUSTER, 1)
+if os.environ.get("NDTPSO_AB_NPT"):
+    ctx.set_option(capi.OPT_POINTS_PER_THREAD, int(os.environ["NDTPSO_AB_NPT"]))
 bt = ctx.batch(workload.cfg2_batch(batch), capi.PsoConfig.make(population=70, iterations=50))
 ts = []
 for _ in range(6):

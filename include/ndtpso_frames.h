@@ -57,6 +57,11 @@ void ndtpso_frame_last_h2d_bytes(const ndtpso_frame* f, int64_t* align_bytes, in
 /* the device's copy of the table (builds it first; synchronises): mean [C][2], inv_cov [C][4], built [C]; NDTPSO_ERR_ARG without a mirror */
 int ndtpso_frame_download_device_map(ndtpso_frame* f, double* mean, double* inv_cov, uint8_t* built);
 
+/* What a failure of the device path does (pso_set_failure_handler of the drop-in's core.h; the reference's CPU path cannot fail).
+ * 0 (default): the failing call reports an error (C++: throws std::runtime_error).  1: the failure is recorded for
+ * ndtpso_frame_last_error, the call succeeds with its neutral result — align / glir return the caller's guess, cost returns 0 — and
+ * ndtpso_frame_last_cost is NaN until the next successful call. */
+void ndtpso_frame_set_failure_mode(int keep_going);
 double ndtpso_frame_last_cost(void);
 const char* ndtpso_frame_last_error(void);
 

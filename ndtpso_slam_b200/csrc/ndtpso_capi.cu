@@ -78,6 +78,7 @@ struct ndtpso_ctx {
   int max_smem_optin = 0;
   std::vector<PoolBuf> dev_pool, pin_pool;
   int smem_attr_set[33] = {0};
+  std::vector<const void*> sliced_attr_set;  // point-sliced kernel instances whose function attributes are set on this context's device
 };
 
 struct ndtpso_exchange {
@@ -710,11 +711,12 @@ template <int NPT, int JB, int CL, int MAXT, int MINB>
 int launch_sliced_cfg(ndtpso_batch* bt, int nw, int groups, int smem, bool screen = false) {
   ndtpso_ctx* ctx = bt->ctx;
   auto kern = pso_sliced_kernel<NPT, JB, CL, MAXT, MINB>;
-  static bool attr_set[64] = {false};
-  if (!attr_set[ctx->device & 63]) {
+  // function attributes are per device; remembered per context (a context never changes its device)
+  const void* kern_id = reinterpret_cast<const void*>(kern);
+  if (std::find(ctx->sliced_attr_set.begin(), ctx->sliced_attr_set.end(), kern_id) == ctx->sliced_attr_set.end()) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
     if (CL > 8) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set[ctx->device & 63] = true;
+    ctx->sliced_attr_set.push_back(kern_id);
   }
   PsoParams prm = bt->prm;
   prm.smem_bytes = smem;

@@ -35,6 +35,15 @@ double cost_function(Vector3d trans, NDTFrame* const ref_frame, const NDTFrame* 
 // best cost of the most recent pso_optimization call (the reference only prints it, core.cpp:111-114)
 double pso_last_cost();
 
+// Extension (not in the reference, whose CPU path cannot fail): what happens when the device path fails — no usable CUDA
+// device, a CUDA error, the pools of a device-resident map exhausted.  Without a handler (the default) the failing call throws
+// std::runtime_error: there is no CPU fallback, and a wrong pose must not pass for a match.  With a handler installed it is
+// called with the message; if it returns, pso_optimization / glir_pso_optimization / NDTFrame::align return the caller's
+// initial guess ("no correction for this scan"), cost_function returns 0 (the cost of a scan that hits no built cell), and
+// pso_last_cost() is NaN until the next successful call.  Returns the previous handler.
+typedef void (*pso_failure_handler)(const char* what);
+pso_failure_handler pso_set_failure_handler(pso_failure_handler handler);
+
 // (x, y) rotated by trans.z() and shifted by (trans.x(), trans.y())
 inline Vector2d transform_point(const Vector2d& point, const Vector3d& trans) {
   const double c = std::cos(trans.z()), s = std::sin(trans.z());

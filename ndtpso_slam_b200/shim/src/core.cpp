@@ -1,8 +1,9 @@
 // pso_optimization / cost_function of the drop-in library: flatten the two frames into the C ABI's
 // POD views (zero-copy for the map table) and run on the GPU.  There is no CPU fallback: if the
-// device path fails the process is told so and stops, like any other fatal runtime error.
+// device path fails the call throws, unless the application installed a failure handler (core.h).
 #include "ndtpso_slam/core.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -14,12 +15,18 @@ namespace {
 
 ndtpso_ctx* g_ctx = nullptr;
 double g_last_cost = 0.;
+int g_ctx_status = NDTPSO_OK;
+pso_failure_handler g_on_failure = nullptr;
 
-ndtpso_ctx* context() {
+// the process-wide context; nullptr without a usable CUDA device (g_ctx_status says why)
+ndtpso_ctx* context_or_null() {
   if (!g_ctx) {
     const char* dev = std::getenv("NDTPSO_DEVICE");
-    const int rc = ndtpso_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx);
-    if (rc != NDTPSO_OK) throw std::runtime_error("ndtpso_b200: no usable CUDA device (status " + std::to_string(rc) + "); there is no CPU path");
+    g_ctx_status = ndtpso_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx);
+    if (g_ctx_status != NDTPSO_OK) {
+      g_ctx = nullptr;
+      return nullptr;
+    }
     std::atexit([]() {
       ndtpso_ctx_destroy(g_ctx);
       g_ctx = nullptr;
@@ -31,21 +38,37 @@ ndtpso_ctx* context() {
 }  // namespace
 
 namespace ndtpso_b200 {
-// the process-wide context of the drop-in library; nullptr (no exception) without a usable CUDA device
-ndtpso_ctx* shim_context_or_null() {
-  try {
-    return context();
-  } catch (const std::exception&) {
-    return nullptr;
-  }
-}
+ndtpso_ctx* shim_context_or_null() { return context_or_null(); }
 void shim_set_last_cost(double c) { g_last_cost = c; }
+// The device path failed: throws unless a failure handler is installed (core.h); if the handler returns, so does this
+// function, and the caller hands back its neutral result.
+void shim_fail(const std::string& what) {
+  g_last_cost = std::nan("");
+  if (!g_on_failure) throw std::runtime_error(what);
+  g_on_failure(what.c_str());
+}
 }  // namespace ndtpso_b200
+
+pso_failure_handler pso_set_failure_handler(pso_failure_handler handler) {
+  const pso_failure_handler old = g_on_failure;
+  g_on_failure = handler;
+  return old;
+}
 
 namespace {
 
-void check(int rc, const char* what) {
-  if (rc != NDTPSO_OK) throw std::runtime_error(std::string("ndtpso_b200: ") + what + ": " + ndtpso_last_error(g_ctx));
+// the context, or nullptr after reporting why there is none
+ndtpso_ctx* context() {
+  ndtpso_ctx* ctx = context_or_null();
+  if (!ctx) ndtpso_b200::shim_fail("ndtpso_b200: no usable CUDA device (status " + std::to_string(g_ctx_status) + "); there is no CPU path");
+  return ctx;
+}
+
+// true when rc is a failure (reported; the caller returns its neutral result)
+bool failed(int rc, const char* what) {
+  if (rc == NDTPSO_OK) return false;
+  ndtpso_b200::shim_fail(std::string("ndtpso_b200: ") + what + ": " + ndtpso_last_error(g_ctx));
+  return true;
 }
 
 void fill_problem(ndtpso_problem* p, NDTFrame* ref_frame, const NDTFrame* new_frame) {
@@ -67,6 +90,7 @@ namespace {
 
 Vector3d solve(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* new_frame, const Array3d& deviation, const ndtpso_pso_config& cf) {
   ndtpso_ctx* ctx = context();
+  if (!ctx) return initial_guess;
   ndtpso_problem p;
   fill_problem(&p, ref_frame, new_frame);
   for (int k = 0; k < 3; ++k) {
@@ -80,7 +104,7 @@ Vector3d solve(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* new_
   p.rand_stream = stream.data();
   p.rand_count = n;
   double pose[3], cost = 0.;
-  check(ndtpso_align_batch(ctx, 1, &p, &cf, pose, &cost), "ndtpso_align_batch");
+  if (failed(ndtpso_align_batch(ctx, 1, &p, &cf, pose, &cost), "ndtpso_align_batch")) return initial_guess;
   g_last_cost = cost;
   return Vector3d(pose[0], pose[1], pose[2]);
 }
@@ -112,11 +136,12 @@ Vector3d glir_pso_optimization(Vector3d initial_guess, NDTFrame* ref_frame, NDTF
 
 double cost_function(Vector3d trans, NDTFrame* const ref_frame, const NDTFrame* const new_frame) {
   ndtpso_ctx* ctx = context();
+  if (!ctx) return 0.;
   ndtpso_problem p;
   fill_problem(&p, ref_frame, new_frame);
   const double pose[3] = {trans.x(), trans.y(), trans.z()};
   double cost = 0.;
-  check(ndtpso_cost_batch(ctx, 1, &p, 1, pose, &cost), "ndtpso_cost_batch");
+  if (failed(ndtpso_cost_batch(ctx, 1, &p, 1, pose, &cost), "ndtpso_cost_batch")) return 0.;
   return cost;
 }
 

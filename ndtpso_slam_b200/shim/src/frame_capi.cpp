@@ -114,6 +114,10 @@ int ndtpso_frame_download_device_map(ndtpso_frame* f, double* mean, double* inv_
   const int rc = guarded([&]() { ok = f->frame.downloadDeviceMap(mean, inv_cov, built) ? 1 : 0; });
   return rc != NDTPSO_OK ? rc : (ok ? NDTPSO_OK : NDTPSO_ERR_ARG);
 }
+void ndtpso_frame_set_failure_mode(int keep_going) {
+  // keep_going: a failure of the device path is recorded (ndtpso_frame_last_error) and the call returns its neutral result
+  pso_set_failure_handler(keep_going ? +[](const char* what) { g_err = what; } : nullptr);
+}
 double ndtpso_frame_last_cost(void) { return pso_last_cost(); }
 const char* ndtpso_frame_last_error(void) { return g_err.c_str(); }
 

@@ -22,6 +22,7 @@
 namespace ndtpso_b200 {
 ndtpso_ctx* shim_context_or_null();
 void shim_set_last_cost(double c);
+void shim_fail(const std::string& what);
 }  // namespace ndtpso_b200
 
 struct NDTFrame::DeviceMirror {
@@ -169,11 +170,16 @@ bool NDTFrame::mirrorAlign(const Vector3d& guess, const NDTFrame* new_frame, con
   double pose[3], cost = 0.;
   if (ndtpso_dframes_align_streams(d.df, g, &cf, stream.data(), pose, &cost) != NDTPSO_OK) {
     // the numbers are drawn: hand the call to the upload path would draw them again and leave the stream out of step, so fail loudly
-    throw std::runtime_error(std::string("ndtpso_b200: device-resident align failed: ") + ndtpso_last_error(ndtpso_b200::shim_context_or_null()));
+    ndtpso_b200::shim_fail(std::string("ndtpso_b200: device-resident align failed: ") + ndtpso_last_error(ndtpso_b200::shim_context_or_null()));
+    *pose_out = guess;  // a failure handler took it: no correction for this scan
+    return true;
   }
   int32_t flags = 0;
-  if (ndtpso_dframes_status(d.df, &flags) == NDTPSO_OK && (flags & (NDTPSO_DF_CELL_POOL_FULL | NDTPSO_DF_WINDOW_TRUNCATED)))
-    throw std::runtime_error("ndtpso_b200: the device-resident map outgrew its pools (raise NDTPSO_SHIM_MAX_CELLS / NDTPSO_SHIM_WINDOW_POINTS, or set NDTPSO_SHIM_DEVICE_MAP=0)");
+  if (ndtpso_dframes_status(d.df, &flags) == NDTPSO_OK && (flags & (NDTPSO_DF_CELL_POOL_FULL | NDTPSO_DF_WINDOW_TRUNCATED))) {
+    ndtpso_b200::shim_fail("ndtpso_b200: the device-resident map outgrew its pools (raise NDTPSO_SHIM_MAX_CELLS / NDTPSO_SHIM_WINDOW_POINTS, or set NDTPSO_SHIM_DEVICE_MAP=0)");
+    *pose_out = guess;
+    return true;
+  }
   ndtpso_b200::shim_set_last_cost(cost);
   last_align_h2d_ = h2d + 4 * static_cast<size_t>(n) + 24;
   *pose_out = Vector3d(pose[0], pose[1], pose[2]);

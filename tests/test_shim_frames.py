@@ -238,3 +238,33 @@ def test_frames_built_without_align_never_touch_the_device():
     assert ref.map_table()["built"].sum() > 0
     ref.close()
     q.close()
+
+
+def test_failure_mode_without_a_device():
+    """Extension of the drop-in (core.h, pso_set_failure_handler): the reference's CPU path cannot fail, the device path can.  By
+    default a failed align is an error (C++: an exception); with the failure mode set the call hands back the caller's guess and
+    records why.  Checked where it can be provoked at will: on a machine without a CUDA device."""
+    import math
+    from ndtpso_slam_b200 import capi
+    if capi.load_library().ndtpso_device_count() > 0:
+        pytest.skip("needs a machine without a CUDA device")
+    L = frames.load_library()
+    ref = frames.Frame(width=20, height=20, cell_side=1.0, calculate_cells_params=True)
+    scan = frames.Frame(width=20, height=20, cell_side=20.0, calculate_cells_params=False)
+    r = np.full(61, 4.0, dtype=np.float32)
+    scan.load_laser(r, -1.0, 2.0 / 60, 30.0)
+    ref.update((0., 0., 0.), scan)
+    guess = (0.1, -0.2, 0.03)
+    try:
+        with pytest.raises(capi.NdtpsoError, match="no usable CUDA device"):
+            ref.align(guess, scan)
+        L.ndtpso_frame_set_failure_mode(1)
+        pose = ref.align(guess, scan)
+        assert np.array_equal(pose, np.array(guess))
+        assert math.isnan(L.ndtpso_frame_last_cost())
+        assert b"no usable CUDA device" in L.ndtpso_frame_last_error()
+        assert ref.cost(scan, guess) == 0.0
+    finally:
+        L.ndtpso_frame_set_failure_mode(0)
+        ref.close()
+        scan.close()

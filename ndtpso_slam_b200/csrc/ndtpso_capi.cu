@@ -824,7 +824,10 @@ int launch_sliced(ndtpso_batch* bt) {
     if (bt->n * 16 <= ctx->sm_count) rc = try_cluster<16>(bt, false);
     if (rc == 1 && bt->n * 8 <= ctx->sm_count) rc = try_cluster<8>(bt, false);
     if (rc == 1 && bt->n * 4 <= ctx->sm_count) rc = try_cluster<4>(bt, false);
-    if (rc == 1) rc = try_cluster<2>(bt, false);
+    // a cluster of two (unscreened) loses to one screened CTA per problem (profiles/r02c_cluster_sizes.txt: 64 problems 1.69 vs 1.47 ms):
+    // only for batches the screen does not take
+    PsoParams probe{};
+    if (rc == 1 && !(ctx->opt_screen != 0 && screen_params(bt, &probe, true))) rc = try_cluster<2>(bt, false);
     if (rc != 1) return rc;
   }
   int npt = 0, nw = 0;

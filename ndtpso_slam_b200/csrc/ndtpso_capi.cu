@@ -35,6 +35,7 @@ using namespace ndtpso;
 
 namespace {
 
+constexpr int kMaxChunks = 8;  // pipeline chunks of one ndtpso_align_batch call
 struct PoolBuf {
   void* ptr;
   size_t bytes;
@@ -56,7 +57,7 @@ struct ndtpso_ctx {
   int opt_host_threads = 0;  // staging threads incl. the caller: 0 = auto (the cores this process may use, at most 8)
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
-  cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // pipelined align_batch
+  cudaStream_t chunk_stream[kMaxChunks] = {};  // pipelined align_batch
   cudaStream_t copy_stream = nullptr;  // uploads of batch k+1 overlap the kernels of batch k
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};  // ndtpso_align_submit alternates between them (see there)
   unsigned pipe_next = 0;
@@ -1066,7 +1067,7 @@ int ndtpso_ctx_set_option(ndtpso_ctx* ctx, int option, int64_t value) {
       ctx->opt_kernel = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_PIPELINE_CHUNKS:
-      if (value < 0 || value > 4) return fail(ctx, NDTPSO_ERR_ARG, "pipeline chunks must be in 0..4 (0 = auto)");
+      if (value < 0 || value > kMaxChunks) return fail(ctx, NDTPSO_ERR_ARG, "pipeline chunks must be in 0..8 (0 = auto)");
       ctx->opt_chunks = (int)value;
       return NDTPSO_OK;
     case NDTPSO_OPT_CANDIDATE_BATCH:
@@ -1273,7 +1274,7 @@ int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problem
   // auto: three chunks from 128 problems on (tools/onecall_chunks.py, one B200, cfg2: 128 problems 2.71 -> 2.36 ms per call,
   // 256: 3.91 -> 3.21, 512: 6.84 -> 5.71; no difference at 64)
   const int want = ctx->opt_chunks > 0 ? ctx->opt_chunks : (n >= 128 ? 3 : 1);
-  const int chunks = (ctx->stream == ctx->own_stream && n >= 64) ? std::min(want, n / 32) : 1;
+  const int chunks = (ctx->stream == ctx->own_stream && n >= 64) ? std::min(std::min(want, kMaxChunks), n / 32) : 1;
   if (chunks <= 1) {
     ndtpso_batch* bt = nullptr;
     int rc = batch_create_impl(ctx, n, problems, conf, true, &bt);  // built cells only cross PCIe
@@ -1284,8 +1285,8 @@ int ndtpso_align_batch(ndtpso_ctx* ctx, int32_t n, const ndtpso_problem* problem
     return rc;
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  ndtpso_batch* bts[4] = {nullptr, nullptr, nullptr, nullptr};
-  int lo[5];
+  ndtpso_batch* bts[kMaxChunks] = {};
+  int lo[kMaxChunks + 1];
   for (int k = 0; k <= chunks; ++k) lo[k] = (int)((int64_t)n * k / chunks);
   int rc = NDTPSO_OK;
   int64_t h2d = 0;

@@ -8,7 +8,7 @@ ctx = capi.Context(0)
 for B in (64, 128, 192, 256, 296, 512):
     ps = capi.ProblemSet(workload.cfg2_batch(B))
     row = []
-    for ch in (1, 2, 3, 4):
+    for ch in (1, 2, 3, 4, 6, 8):
         ctx.set_option(capi.OPT_PIPELINE_CHUNKS, ch)
         for _ in range(3):
             ctx.align_batch(ps, conf)
@@ -16,4 +16,4 @@ for B in (64, 128, 192, 256, 296, 512):
         for _ in range(8):
             t0 = time.perf_counter(); ctx.align_batch(ps, conf); ts.append(time.perf_counter() - t0)
         row.append(1e3 * float(np.median(ts)))
-    print(f"B={B:4d}: " + "  ".join(f"chunks {c}: {t:.3f} ms" for c, t in zip((1, 2, 3, 4), row)), flush=True)
+    print(f"B={B:4d}: " + "  ".join(f"chunks {c}: {t:.3f} ms" for c, t in zip((1, 2, 3, 4, 6, 8), row)), flush=True)

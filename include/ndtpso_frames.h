@@ -57,6 +57,10 @@ void ndtpso_frame_last_h2d_bytes(const ndtpso_frame* f, int64_t* align_bytes, in
 /* the device's copy of the table (builds it first; synchronises): mean [C][2], inv_cov [C][4], built [C]; NDTPSO_ERR_ARG without a mirror */
 int ndtpso_frame_download_device_map(ndtpso_frame* f, double* mean, double* inv_cov, uint8_t* built);
 
+/* The next n outputs of the process-global rand(), advancing it by exactly n draws: how the drop-in's align takes the
+ * 3 + 3P + 6PI numbers the reference would draw (core.cpp:14,58-69,84) — from glibc's own state table, without n trips through
+ * its lock; falls back to n calls of rand() wherever that is not possible (NDTPSO_SHIM_FAST_RAND=0 forces the fallback). */
+void ndtpso_frame_draw_rand(int32_t* out, int64_t n);
 /* What a failure of the device path does (pso_set_failure_handler of the drop-in's core.h; the reference's CPU path cannot fail).
  * 0 (default): the failing call reports an error (C++: throws std::runtime_error).  1: the failure is recorded for
  * ndtpso_frame_last_error, the call succeeds with its neutral result — align / glir return the caller's guess, cost returns 0 — and

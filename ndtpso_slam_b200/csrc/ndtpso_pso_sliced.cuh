@@ -634,6 +634,35 @@ __device__ __forceinline__ void score_batch(const SliceCtx& m, const double2 (&p
   if (packed_writer<JB>(lane) && jj < hi) wpart[jj * NW + warp] = tot;
 }
 
+// two batches of JB candidates at once (cluster form: one CTA per SM, registers to spare, few warps to hide the fp64 latency):
+// 2 JB NPT independent evaluations in flight per lane, the two packed reductions interleave
+template <int NPT, int JB, bool FAST_GEOM, int VAR>
+__device__ __forceinline__ void score_batch_pair(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, int j, int NW,
+                                                 int warp, int lane) {
+  double acc0[JB], acc1[JB];
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+    const Pose* p0 = pose + j + b;
+    const Pose* p1 = pose + j + JB + b;
+    const double2 t0 = *reinterpret_cast<const double2*>(&p0->x), c0 = *reinterpret_cast<const double2*>(&p0->c);
+    const double2 t1 = *reinterpret_cast<const double2*>(&p1->x), c1 = *reinterpret_cast<const double2*>(&p1->c);
+    acc0[b] = 0.;
+    acc1[b] = 0.;
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      slice_point<FAST_GEOM, VAR>(m, pt[k], t0.x, t0.y, c0.x, c0.y, acc0[b]);
+      slice_point<FAST_GEOM, VAR>(m, pt[k], t1.x, t1.y, c1.x, c1.y, acc1[b]);
+    }
+  }
+  const double tot0 = packed_warp_sum<JB>(acc0, lane);
+  const double tot1 = packed_warp_sum<JB>(acc1, lane);
+  if (packed_writer<JB>(lane)) {
+    const int jj = j + packed_slot<JB>(lane);
+    wpart[jj * NW + warp] = tot0;
+    wpart[(jj + JB) * NW + warp] = tot1;
+  }
+}
+
 template <int NPT, int JB, int CL, bool FAST_GEOM, int VAR>
 __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double2 (&pt)[NPT], const Pose* pose, double* wpart, int lo,
                                                  int hi, const Topo& tp, int warp, int lane) {
@@ -642,8 +671,23 @@ __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double
     int j = lo;
     for (; j + 4 <= hi; j += 4) score_batch<NPT, 4, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
     for (; j < hi; j += 2) score_batch<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
+  } else if (CL > 1) {
+    // cluster form: group g scores an equal, contiguous share of the pending candidates (70 on 4 groups = 18 + 18 + 18 + 16), whole
+    // batches of JB first and the rest in batches of 4 and 2: every group's critical path is the same two-and-a-bit batches
+    // (dealing whole batches of 8 round-robin gave one group three batches and the others two, and all waited for the one)
+    const int q = (hi - lo + tp.G - 1) / tp.G;
+    int j = lo + tp.g * q;
+    const int ghi = min(j + q, hi);
+    for (; j + 2 * JB <= ghi; j += 2 * JB) score_batch_pair<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, wpart, j, tp.NW, warp, lane);
+    for (; j + JB <= ghi; j += JB) score_batch<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, wpart, j, ghi, tp.NW, warp, lane);
+    if (JB > 4)
+      for (; j + 4 <= ghi; j += 4) score_batch<NPT, 4, FAST_GEOM, VAR>(m, pt, pose, wpart, j, ghi, tp.NW, warp, lane);
+    if (JB > 2)
+      for (; j < ghi; j += 2) score_batch<NPT, 2, FAST_GEOM, VAR>(m, pt, pose, wpart, j, ghi, tp.NW, warp, lane);
+    else
+      for (; j < ghi; j += JB) score_batch<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, wpart, j, ghi, tp.NW, warp, lane);
   } else {
-    for (int j = lo + tp.g * JB; j < hi; j += JB * tp.G) score_batch<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
+    for (int j = lo; j < hi; j += JB) score_batch<NPT, JB, FAST_GEOM, VAR>(m, pt, pose, wpart, j, hi, tp.NW, warp, lane);
   }
 }
 
@@ -653,17 +697,16 @@ __device__ __forceinline__ void score_candidates(const SliceCtx& m, const double
 template <int JB, int CL>
 __device__ __forceinline__ void exchange_partials(const double* wpart, double* cpart, int lo, int hi, const Topo& tp) {
   __syncthreads();
-  const int span = JB * tp.G;
-  const int mine = ((hi - lo + span - 1) / span) * JB;  // candidates of my group, padding included
+  const int q = (hi - lo + tp.G - 1) / tp.G;  // my group's share: see score_candidates
+  const int glo = lo + tp.g * q;
+  const int mine = max(min(glo + q, hi) - glo, 0);
   for (int idx = threadIdx.x; idx < mine * CL; idx += blockDim.x) {
     const int jl = idx / CL, dest = idx - jl * CL;
-    const int j = lo + tp.g * JB + (jl / JB) * span + (jl % JB);
-    if (j < hi) {
-      const double* p = wpart + j * tp.NW;
-      double c = 0.;
-      for (int w = 0; w < tp.NW; ++w) c += p[w];
-      st_cluster_f64(cpart + j * tp.S + tp.s, dest, c);
-    }
+    const int j = glo + jl;
+    const double* p = wpart + j * tp.NW;
+    double c = 0.;
+    for (int w = 0; w < tp.NW; ++w) c += p[w];
+    st_cluster_f64(cpart + j * tp.S + tp.s, dest, c);
   }
   cluster_barrier();
 }

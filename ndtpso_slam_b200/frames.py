@@ -58,6 +58,8 @@ def load_library():
     L.ndtpso_frame_last_h2d_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ndtpso_frame_last_h2d_bytes.restype = None
     L.ndtpso_frame_download_device_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ndtpso_frame_draw_rand.argtypes = [C.POINTER(C.c_int32), C.c_int64]
+    L.ndtpso_frame_draw_rand.restype = None
     L.ndtpso_frame_set_failure_mode.argtypes = [C.c_int]
     L.ndtpso_frame_set_failure_mode.restype = None
     L.ndtpso_frame_last_cost.restype = C.c_double
@@ -71,7 +73,7 @@ EXPORTS = ["ndtpso_frame_new", "ndtpso_frame_free", "ndtpso_frame_load_laser", "
            "ndtpso_frame_is_built", "ndtpso_frame_reset_cells", "ndtpso_frame_map_view", "ndtpso_frame_sparse_map_view", "ndtpso_frame_scan_points",
            "ndtpso_frame_point_count", "ndtpso_frame_add_pose", "ndtpso_frame_dump_map", "ndtpso_frame_align", "ndtpso_frame_align_conf", "ndtpso_frame_glir", "ndtpso_frame_cost", "ndtpso_frame_last_cost",
            "ndtpso_frame_device_resident", "ndtpso_frame_last_h2d_bytes", "ndtpso_frame_download_device_map",
-           "ndtpso_frame_set_failure_mode", "ndtpso_frame_last_error"]
+           "ndtpso_frame_draw_rand", "ndtpso_frame_set_failure_mode", "ndtpso_frame_last_error"]
 
 
 def _d3(v):

@@ -5,9 +5,12 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "ndtpso_b200.h"
 
@@ -46,6 +49,80 @@ void shim_fail(const std::string& what) {
   g_last_cost = std::nan("");
   if (!g_on_failure) throw std::runtime_error(what);
   g_on_failure(what.c_str());
+}
+}  // namespace ndtpso_b200
+
+namespace ndtpso_b200 {
+// The next n outputs of the process-global std::rand(), which is advanced by exactly n draws — what n calls of rand() do, without
+// n trips through glibc's lock (9 093 draws per default align: ~0.15 ms of a 0.7 ms callback).
+// glibc keeps rand()'s state in a table the public API hands out: setstate() switches to another table and returns the previous
+// one, having saved the generator's position in its first word ((rear index) * 5 + type).  For the default TYPE_3 generator
+// (additive feedback, degree 31, separation 3: r[i] = r[i-31] + r[i-3], output = r[i] >> 1) the table is advanced here and
+// handed back with setstate().  The first use checks itself against rand() on the same state; anything unexpected (another
+// libc, another generator type, NDTPSO_SHIM_FAST_RAND=0) falls back to calling rand() n times.  Like rand() itself this is for
+// one drawing thread at a time: a thread that calls rand() during the switch would draw from the scratch table.
+void shim_draw_rand(int32_t* out, size_t n) {
+#if defined(__GLIBC__)
+  static int mode = -1;  // -1 untested, 0 off, 1 on
+  alignas(8) static char scratch[128];
+  static bool scratch_ready = false;
+  if (mode == -1) {
+    const char* e = std::getenv("NDTPSO_SHIM_FAST_RAND");
+    if (e && std::atoi(e) == 0) mode = 0;
+  }
+  auto advance = [](int32_t* w, int32_t* dst, size_t m) {  // w = the table (first word: position and type)
+    int32_t* st = w + 1;
+    int r = w[0] / 5, f = (r + 3) % 31;
+    for (size_t i = 0; i < m; ++i) {
+      const uint32_t v = static_cast<uint32_t>(st[f]) + static_cast<uint32_t>(st[r]);
+      st[f] = static_cast<int32_t>(v);
+      dst[i] = static_cast<int32_t>(v >> 1);
+      if (++f == 31) f = 0;
+      if (++r == 31) r = 0;
+    }
+    w[0] = 5 * r + 3;
+  };
+  if (mode != 0 && n > 0) {
+    char* old = scratch_ready ? setstate(scratch) : initstate(1u, scratch, sizeof scratch);
+    scratch_ready = true;
+    int32_t* w = reinterpret_cast<int32_t*>(old);
+    const bool type3 = old && (w[0] % 5) == 3 && w[0] >= 0 && w[0] / 5 < 31;
+    if (type3 && mode == -1) {
+      // self-check: four draws from a copy of the table must be the four draws rand() then makes from the table itself
+      int32_t copy[32], mine[4];
+      std::memcpy(copy, w, sizeof copy);
+      advance(copy, mine, 4);
+      setstate(old);
+      const size_t k = n < 4 ? n : 4;
+      bool same = true;
+      for (size_t i = 0; i < 4; ++i) {
+        const int32_t v = std::rand();
+        same = same && v == mine[i];
+        if (i < k) out[i] = v;
+      }
+      // (a request for fewer than four numbers has now drawn four: cannot happen, a PSO call draws at least three + six)
+      mode = same ? 1 : 0;
+      for (size_t i = 4; i < n; ++i) out[i] = 0;
+      if (n <= 4) return;
+      out += 4;
+      n -= 4;
+      if (mode == 0) {
+        for (size_t i = 0; i < n; ++i) out[i] = std::rand();
+        return;
+      }
+      old = setstate(scratch);
+      w = reinterpret_cast<int32_t*>(old);
+    }
+    if (type3 && mode == 1) {
+      advance(w, out, n);
+      setstate(old);
+      return;
+    }
+    if (old) setstate(old);
+    if (!type3) mode = 0;
+  }
+#endif
+  for (size_t i = 0; i < n; ++i) out[i] = std::rand();
 }
 }  // namespace ndtpso_b200
 
@@ -100,7 +177,7 @@ Vector3d solve(Vector3d initial_guess, NDTFrame* ref_frame, const NDTFrame* new_
   // the reference's random numbers: the next 3 + 3P + 6PI (GLIR: 3(P + 2) + 6PI) outputs of the process-global std::rand()
   const int64_t n = ndtpso_rand_draws(&cf);
   std::vector<int32_t> stream(static_cast<size_t>(n));
-  for (auto& r : stream) r = std::rand();
+  ndtpso_b200::shim_draw_rand(stream.data(), stream.size());
   p.rand_stream = stream.data();
   p.rand_count = n;
   double pose[3], cost = 0.;

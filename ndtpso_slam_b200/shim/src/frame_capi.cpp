@@ -13,6 +13,9 @@ struct ndtpso_frame {
       : frame(Vector3d(t[0], t[1], t[2]), static_cast<unsigned short>(w), static_cast<unsigned short>(h), side, zero) {}
 };
 
+namespace ndtpso_b200 {
+void shim_draw_rand(int32_t* out, size_t n);
+}
 namespace {
 std::string g_err;
 template <class F>
@@ -113,6 +116,9 @@ int ndtpso_frame_download_device_map(ndtpso_frame* f, double* mean, double* inv_
   int ok = 0;
   const int rc = guarded([&]() { ok = f->frame.downloadDeviceMap(mean, inv_cov, built) ? 1 : 0; });
   return rc != NDTPSO_OK ? rc : (ok ? NDTPSO_OK : NDTPSO_ERR_ARG);
+}
+void ndtpso_frame_draw_rand(int32_t* out, int64_t n) {
+  if (out && n > 0) ndtpso_b200::shim_draw_rand(out, static_cast<size_t>(n));
 }
 void ndtpso_frame_set_failure_mode(int keep_going) {
   // keep_going: a failure of the device path is recorded (ndtpso_frame_last_error) and the call returns its neutral result

@@ -23,6 +23,7 @@ namespace ndtpso_b200 {
 ndtpso_ctx* shim_context_or_null();
 void shim_set_last_cost(double c);
 void shim_fail(const std::string& what);
+void shim_draw_rand(int32_t* out, size_t n);
 }  // namespace ndtpso_b200
 
 struct NDTFrame::DeviceMirror {
@@ -165,7 +166,7 @@ bool NDTFrame::mirrorAlign(const Vector3d& guess, const NDTFrame* new_frame, con
   // the reference's random numbers: the next 3 + 3P + 6PI outputs of the process-global std::rand()
   const int64_t n = ndtpso_rand_draws(&cf);
   std::vector<int32_t> stream(static_cast<size_t>(n));
-  for (auto& r : stream) r = std::rand();
+  ndtpso_b200::shim_draw_rand(stream.data(), stream.size());
   const double g[3] = {guess.x(), guess.y(), guess.z()};
   double pose[3], cost = 0.;
   if (ndtpso_dframes_align_streams(d.df, g, &cf, stream.data(), pose, &cost) != NDTPSO_OK) {

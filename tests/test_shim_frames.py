@@ -268,3 +268,24 @@ def test_failure_mode_without_a_device():
         L.ndtpso_frame_set_failure_mode(0)
         ref.close()
         scan.close()
+
+
+@pytest.mark.parametrize("seed", [1, 42, 123456789, 4000000000])
+def test_fast_rand_draw_is_the_process_global_stream(seed):
+    """The drop-in draws an align's random numbers straight from glibc's rand() state (shim_draw_rand, shim/src/core.cpp): the same
+    numbers n calls of rand() return, and rand() afterwards continues as if it had been called n times (core.cpp:14,58-69,84)."""
+    L = frames.load_library()
+    libc = C.CDLL("libc.so.6")
+    libc.rand.restype = C.c_int
+    for n in (9, 35, 9093, 21213):
+        libc.srand(C.c_uint(seed))
+        for _ in range(7):
+            libc.rand()
+        want = [libc.rand() for _ in range(n + 5)]
+        libc.srand(C.c_uint(seed))
+        for _ in range(7):
+            libc.rand()
+        got = (C.c_int32 * n)()
+        L.ndtpso_frame_draw_rand(got, n)
+        assert list(got) == want[:n]
+        assert [libc.rand() for _ in range(5)] == want[n:]

@@ -74,7 +74,7 @@ enum {
   NDTPSO_DF_CELL_POOL_FULL = 1,   /* more than max_cells cells received points: later cells were dropped */
   NDTPSO_DF_WINDOW_TRUNCATED = 2, /* a re-opened window slot's old points had already left the ring */
   NDTPSO_DF_INDEX_PAST_END = 4,   /* a point's flat cell index fell past the table (undefined in the reference): dropped */
-  NDTPSO_DF_IRREGULAR_SIGMA = 8   /* some Sigma^-1 is not finite / symmetric / PSD: the generic PSO kernel is used */
+  NDTPSO_DF_IRREGULAR_SIGMA = 8   /* some Sigma^-1 of the table as the last build left it is not finite / symmetric / PSD: the generic PSO kernel is used (recomputed by every build; the other bits are sticky) */
 };
 
 /* how ndtpso_dframes_align draws its random numbers */

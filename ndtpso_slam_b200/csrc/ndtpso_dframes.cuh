@@ -318,6 +318,10 @@ __global__ void __launch_bounds__(kDfBuildThreads) frame_build_kernel(DevFrames 
   double* icov = F.icov + (size_t)b * F.ncells * 4;
   uint8_t* built = F.built + (size_t)b * F.ncells;
   int my_flags = 0;
+  // DF_IRREGULAR_SIGMA describes the table as THIS build leaves it (every created cell is looked at below), so that a frame whose
+  // one odd cell has been rebuilt into a regular one goes back to the point-sliced kernel; the other bits record events and stay
+  if (threadIdx.x == 0) atomicAnd(&F.flags[b], ~DF_IRREGULAR_SIGMA);
+  __syncthreads();
   for (int ci = threadIdx.x; ci < n_created; ci += blockDim.x) {
     const size_t e = pool0 + ci;
     const int cell = F.cell_of[e];
@@ -391,7 +395,13 @@ __global__ void __launch_bounds__(kDfBuildThreads) frame_build_kernel(DevFrames 
       const bool regular = (__double_as_longlong(s01) == __double_as_longlong(s10)) && s00 >= 0. && s11 >= 0. &&
                            (s00 * s11 - s01 * s10 >= 0.) && s00 < 1e300 && s11 < 1e300 && isfinite(mx) && isfinite(my);
       if (!regular) my_flags |= DF_IRREGULAR_SIGMA;
-    }  // else: the cell keeps whatever flag (and table row) it had
+    } else if (built[cell]) {  // the cell keeps its table row: the row still counts
+      const double mx = mean[2 * (size_t)cell], my = mean[2 * (size_t)cell + 1];
+      const double s00 = icov[4 * (size_t)cell], s01 = icov[4 * (size_t)cell + 1], s10 = icov[4 * (size_t)cell + 2], s11 = icov[4 * (size_t)cell + 3];
+      const bool regular = (__double_as_longlong(s01) == __double_as_longlong(s10)) && s00 >= 0. && s11 >= 0. &&
+                           (s00 * s11 - s01 * s10 >= 0.) && s00 < 1e300 && s11 < 1e300 && isfinite(mx) && isfinite(my);
+      if (!regular) my_flags |= DF_IRREGULAR_SIGMA;
+    }
     if (cc > kMaxPerCell) {  // the slot is full: open the next one (ndtcell.cpp:61-65)
       F.slot[e] = (sl + 1) % kWindow;
       F.cur_count[e] = 0;

@@ -357,3 +357,31 @@ def test_device_frames_screen_on_off(reference):
     assert np.array_equal(out[0][0], out[1][0])
     assert (out[0][1][:, 3] == 0).all() and out[1][1][:, 3].sum() > 0
     assert np.abs(out[1][0][-1][:, 0] - 0.09).max() < 0.05  # and the robots were tracked (x advances 3 cm per scan)
+
+
+def test_irregular_sigma_flag_follows_the_table(ctx):
+    """NDTPSO_DF_IRREGULAR_SIGMA (the frame set then takes the generic PSO kernel) describes the table as the last build left it:
+    a cell of three identical points has a zero covariance — determinant 0, a non-finite inverse (ndtcell.cpp:93-111 divides by
+    it) —, and once more points make it a proper Gaussian the flag is gone again; the event bits stay."""
+    from ndtpso_slam_b200 import dframes
+    df = dframes.DeviceFrames(ctx, 1, 20, 20, 1.0, 64)
+    origin = [(0., 0., 0.)]
+    good = np.array([[2.1, 3.1], [2.3, 3.4], [2.6, 3.2], [2.8, 3.7], [2.2, 3.8]])
+    df.set_scan_points([good])
+    df.update(origin)
+    df.build()
+    assert not df.status()[0] & dframes.DF_IRREGULAR_SIGMA
+    df.set_scan_points([np.array([[5.5, 5.5]] * 3)])  # another cell: three times the same point
+    df.update(origin)
+    df.build()
+    assert df.status()[0] & dframes.DF_IRREGULAR_SIGMA
+    m = df.download_map(0)
+    cell = 15 + 20 * 15  # (5.5 + 10) / 1, row 15
+    assert m["built"][cell] and not np.isfinite(m["inv_cov"][cell]).all()
+    df.set_scan_points([np.array([[5.2, 5.3], [5.7, 5.4], [5.4, 5.8], [5.6, 5.1]])])  # the same cell becomes a proper Gaussian
+    df.update(origin)
+    df.build()
+    m = df.download_map(0)
+    assert np.isfinite(m["inv_cov"][cell]).all()
+    assert not df.status()[0] & dframes.DF_IRREGULAR_SIGMA
+    df.close()

@@ -82,7 +82,7 @@ void shim_draw_rand(int32_t* out, size_t n) {
     }
     w[0] = 5 * r + 3;
   };
-  if (mode != 0 && n > 0) {
+  if (mode != 0 && n >= 4) {  // (shorter requests — a swarm without particles — are not worth the switch, and the self-check draws four)
     char* old = scratch_ready ? setstate(scratch) : initstate(1u, scratch, sizeof scratch);
     scratch_ready = true;
     int32_t* w = reinterpret_cast<int32_t*>(old);
@@ -93,17 +93,13 @@ void shim_draw_rand(int32_t* out, size_t n) {
       std::memcpy(copy, w, sizeof copy);
       advance(copy, mine, 4);
       setstate(old);
-      const size_t k = n < 4 ? n : 4;
       bool same = true;
       for (size_t i = 0; i < 4; ++i) {
-        const int32_t v = std::rand();
-        same = same && v == mine[i];
-        if (i < k) out[i] = v;
+        out[i] = std::rand();
+        same = same && out[i] == mine[i];
       }
-      // (a request for fewer than four numbers has now drawn four: cannot happen, a PSO call draws at least three + six)
       mode = same ? 1 : 0;
-      for (size_t i = 4; i < n; ++i) out[i] = 0;
-      if (n <= 4) return;
+      if (n == 4) return;
       out += 4;
       n -= 4;
       if (mode == 0) {

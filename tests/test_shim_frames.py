@@ -277,7 +277,7 @@ def test_fast_rand_draw_is_the_process_global_stream(seed):
     L = frames.load_library()
     libc = C.CDLL("libc.so.6")
     libc.rand.restype = C.c_int
-    for n in (9, 35, 9093, 21213):
+    for n in (3, 4, 9, 35, 9093, 21213):
         libc.srand(C.c_uint(seed))
         for _ in range(7):
             libc.rand()

@@ -518,7 +518,7 @@ __device__ __forceinline__ void screen_batch(const ScreenCtx& m, const ScreenPts
     for (int k = 1; k < NPT; ++k) acc[b] = fmaf(screen_point(m, p.px2[k], p.py2[k], tuv, cs, sc, edge), p.w[k], acc[b]);
     // a point within beta of a cell edge counts as the worst case, exp(.) = 1: if any of this lane's points is, all of them do
     // (each term is <= 1 and the terms already added are >= 0, so adding the lane's point count keeps an upper bound)
-    acc[b] += edge > m.beta_c ? p.wsum : 0.f;
+    acc[b] = fmaf(edge > m.beta_c ? 1.f : 0.f, p.wsum, acc[b]);  // FSET.BF + FFMA
   }
   const float tot = packed_warp_sum_f<JB>(acc, lane);
   const int jj = j + packed_slot<JB>(lane);

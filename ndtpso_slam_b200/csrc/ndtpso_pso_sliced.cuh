@@ -101,7 +101,7 @@ __host__ __device__ inline int sliced_swarm_smem_bytes(int P, int PW, int WP) {
   b += 13 * Pn * (int)sizeof(double);
   return (b + 15) & ~15;
 }
-// The screen's records, n of them (null record included), in blocks of eight: [8 x {l00, l11, -ox, -oy}][8 x {l10, -, -, -}].
+// The screen's records, n of them (null record included), in blocks of eight: [8 x {l00, l11, c0, c1}][8 x {l10, -, -, -}].
 // Record r's first part sits at 256 (r / 8) + 16 (r % 8), its second part 128 bytes further: consecutive records — the
 // neighbouring cells a warp's points fall into — lie in different shared-memory banks (tools/microbench/lds_wavefronts.cu:
 // with whole records 32 bytes apart, records r and r + 4 collide).  20 bytes are loaded per evaluation (LDS.128 + LDS.32): the
@@ -339,18 +339,21 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       U* lies in the same unit interval: fp32 and fp64 agree on the cell (this also covers the frame's border: frames are
 //       whole cells, so a point within du of the border is within du of a cell edge).  Otherwise the point counts as the
 //       worst case, exp(.) = 1.
-//   (3) Offset from the cell's mean, in cell units.  The record stores o~ = fl(o), o = (mu + W/2)/cs - (n + 1/2) in
-//       [-1/2, 1/2] for a mean inside its cell (any o is handled).  The fp64 evaluation's offset is d* = (U* - n) - o; the
-//       screen's is d~ = fl(df - o~) = d* + eps with
-//           |eps| <= du + u|o| + u(1/2 + |o|)(1 + u) <= delta := du + u(2|o| + 0.51),
-//       and |d*_k| <= dmax_k := max(|-1/2 - o_k|, |1/2 - o_k|) (the point is in the cell), |d~_k| <= dmax_k + delta.
+//   (3) Offset from the cell's mean, in cell units: o = (mu + W/2)/cs - (n + 1/2), in [-1/2, 1/2] for a mean inside its cell (any
+//       o is handled).  The fp64 evaluation's offset is d* = (U* - n) - o; the screen works with d^ = df - o (never formed: o is
+//       folded into the constants c0, c1 of (4)), d^ = d* + eps with |eps| <= du <= delta := du + u(2|o| + 0.51) (the larger
+//       delta of the form that subtracted a rounded o explicitly is kept), and |d*_k| <= dmax_k := max(|-1/2 - o_k|, |1/2 - o_k|)
+//       (the point is in the cell), |d^_k| <= dmax_k + delta.
 //   (4) Exponent.  H = (Sigma^-1/2) cs^2 (positive semi-definite: the host only selects this kernel for such tables),
 //       A(d) = d'Hd = |L'd|^2 with H = LL' (Cholesky), so the point's term is -exp(-A(d*)).  For every t in (0, 1) and reals
 //       a, b:  (a - b)^2 >= (1 - t) a^2 - (1/t - 1) b^2   (2ab <= t a^2 + b^2/t); applied to the vectors L'd~ and L'eps,
 //           A(d*) >= (1 - t) A(d~) - (1/t - 1) A(eps),          A(eps) <= hs delta^2,   hs = H00 + 2|H01| + H11.
-//       The screen evaluates z~0 = fl(l~10 d~1 + fl(l~00 d~0)), z~1 = fl(l~11 d~1) with l~ = fl(l sqrt(S)), S below.  Each
-//       product carries at most three roundings, (1 + u)^3 <= 1 + 4u, so |z~_k - sqrt(S) z_k| <= sqrt(S) ez_k with
-//           ez_0 = 4u (l00 (dmax_0 + delta) + |l10| (dmax_1 + delta)),   ez_1 = 4u l11 (dmax_1 + delta),
+//       The screen evaluates z~0 = fl(l~10 df1 + fl(l~00 df0 + c~0)), z~1 = fl(l~11 df1 + c~1) with l~ = fl(l sqrt(S)),
+//       c~0 = fl(-(l00 o0 + l10 o1) sqrt(S)), c~1 = fl(-l11 o1 sqrt(S)) (fp64, rounded once), S below; in exact arithmetic these
+//       are sqrt(S) z_k(d^).  Each term (l~00 df0, c~0, l~10 df1; l~11 df1, c~1) carries at most three roundings,
+//       (1 + u)^3 <= 1 + 4u, and |df_k| <= 1/2, |c0| <= sqrt(S)(l00 |o0| + |l10| |o1|), |c1| = sqrt(S) l11 |o1|, so
+//       |z~_k - sqrt(S) z_k(d^)| <= sqrt(S) ez_k with
+//           ez_0 = 4u (l00 (dmax_0 + delta) + |l10| (dmax_1 + delta)),   ez_1 = 4u l11 (dmax_1 + delta)      (dmax_k = 1/2 + |o_k|),
 //       and again z_k^2 >= (1 - t) z~_k^2/S - (1/t - 1) ez_k^2 (also when |z~_k| < sqrt(S) ez_k: the right side is then <= 0).
 //       xe = fl(-z~1^2 + fl(-z~0^2 + kappa2)) >= kappa2 (1 - 2u') - (z~0^2 + z~1^2)(1 + 2u'), u' = u(1 + u) (the squares
 //       are exact inside the FMAs).  With S = (1 - t)^2 (1 - 2^-22) log2(e) and
@@ -367,7 +370,7 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       degenerate cell costs its own points' terms, not the tightness of the whole table.
 //       The Cholesky factor is computed in fp64 and shrunk by what its own rounding could add (1e-12 relative on l00, l10;
 //       4e-15 H11 absolute on l11^2 before the root, which also covers cancellation in H11 - l10^2).
-//       The null record (unbuilt cell, outside the strip) is {l00 = 1, l11 = 0, -ox = 1e18, -oy = 0, l10 = 0}: z0 = 1e18,
+//       The null record (unbuilt cell, outside the strip) is {l00 = 0, l11 = 0, c0 = 1e18, c1 = 0, l10 = 0}: z0 = 1e18,
 //       xe = kappa2 - 1e36, e = 0 without a test.
 //   (5) Sum.  ex2.approx is within 2 ulp (2^-22); the per-lane accumulation (NPT multiply-adds with weights 0 or 1), the warp tree (5) and the sum over
 //       the warps (NW - 1) are fp32 additions of non-negative terms: relative error <= (NPT + NW + 4) u < 2^-19 for every
@@ -376,7 +379,7 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       for results flushed to zero (ex2.approx.ftz below 2^-126; the fp64 side flushes too, which only raises its cost).
 // cost >= L because each fp64 term is >= -(upper bound of its exponential).
 struct ScreenCtx {
-  // shared: records {l00, l11, -ox, -oy}, {l10, -, -, -} in blocks of eight (screen_rec_bytes) from the 32-bit shared address rec32
+  // shared: records {l00, l11, c0, c1}, {l10, -, -, -} in blocks of eight (screen_rec_bytes) from the 32-bit shared address rec32
   unsigned rec32;
   const unsigned short* grid;  // shared: the 32-bit shared ADDRESS of the cell's record (rec32 + screen_rec_offset(id); below 2^16)
   float beta_c;                // 0.5 - beta
@@ -435,11 +438,10 @@ __device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 p
   // min(g + nbase, span) is one VIADDMNMX
   const unsigned g = __float_as_uint(t2.x) + static_cast<unsigned>(m.gw) * __float_as_uint(t2.y);
   const unsigned ra = m.grid[__viaddmin_u32(g, m.nbase, m.span)];
-  const float4 l = lds_f4(ra);        // l00, l11, -ox, -oy
+  const float4 l = lds_f4(ra);        // l00, l11, c0, c1
   const float l10 = lds_f1_128(ra);
-  const float2 d = __fadd2_rn(df, make_float2(l.z, l.w));
-  const float2 zz = __fmul2_rn(make_float2(l.x, l.y), d);                      // l00 d0, l11 d1
-  const float z0 = fmaf(l10, d.y, zz.x);
+  const float2 zz = __ffma2_rn(make_float2(l.x, l.y), df, make_float2(l.z, l.w));  // l00 df0 + c0, l11 df1 + c1 (= z1)
+  const float z0 = fmaf(l10, df.y, zz.x);
   const float xe = fmaf(-zz.y, zz.y, fmaf(-z0, z0, m.kappa2));
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xe));                       // 2 ulp, results below 2^-126 flushed: covered by the total's slack
@@ -1321,7 +1323,7 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
       if (g < span && r == n_rec) continue;  // unbuilt cell: points at the null record
       float* o = reinterpret_cast<float*>(s_rec32 + screen_rec_offset(r));  // o[0..3] = first part, o[32] = second part (128 bytes on)
       if (r == n_rec) {  // the null record: z0 = 1e18 whatever the point
-        o[0] = 1.f;
+        o[0] = 0.f;
         o[1] = 0.f;
         o[2] = 1e18f;
         o[3] = 0.f;
@@ -1333,10 +1335,12 @@ __device__ __forceinline__ SlicedSmem sliced_prologue(unsigned char* smem_raw, c
       // !(t <= 1/2): this record needs more than the table's kappa2 gives (or is not finite): the trivial bound, e = 2^kappa2
       const double scale = (t <= 0.5) ? sqrt((1. - t) * (1. - t) * (1. - 2.384185791015625e-07) * 1.4426950408889634) * (1. - 1e-12) : 0.;
       // the factor's entries are rounded to fp32 here; that rounding is the first of the three ez counts per product
+      // the offset is folded into the constants of the two rows: z0 = l00 df0 + l10 df1 + c0, z1 = l11 df1 + c1 (computed in fp64,
+      // rounded once: the first of at most three roundings the term carries)
       o[0] = scale > 0. ? static_cast<float>(sr.l00 * scale) : 0.f;
       o[1] = scale > 0. ? static_cast<float>(sr.l11 * scale) : 0.f;
-      o[2] = scale > 0. ? static_cast<float>(-sr.ox) : 0.f;
-      o[3] = scale > 0. ? static_cast<float>(-sr.oy) : 0.f;
+      o[2] = scale > 0. ? static_cast<float>(-(sr.l00 * sr.ox + sr.l10 * sr.oy) * scale) : 0.f;
+      o[3] = scale > 0. ? static_cast<float>(-(sr.l11 * sr.oy) * scale) : 0.f;
       o[32] = scale > 0. ? static_cast<float>(sr.l10 * scale) : 0.f;
     }
     sc->kappa2 = kappa2;

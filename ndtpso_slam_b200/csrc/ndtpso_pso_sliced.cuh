@@ -355,7 +355,7 @@ __device__ __forceinline__ bool packed_writer(int lane) {
 //       |z~_k - sqrt(S) z_k(d^)| <= sqrt(S) ez_k with
 //           ez_0 = 4u (l00 (dmax_0 + delta) + |l10| (dmax_1 + delta)),   ez_1 = 4u l11 (dmax_1 + delta)      (dmax_k = 1/2 + |o_k|),
 //       and again z_k^2 >= (1 - t) z~_k^2/S - (1/t - 1) ez_k^2 (also when |z~_k| < sqrt(S) ez_k: the right side is then <= 0).
-//       xe = fl(-z~1^2 + fl(-z~0^2 + kappa2)) >= kappa2 (1 - 2u') - (z~0^2 + z~1^2)(1 + 2u'), u' = u(1 + u) (the squares
+//       xe = fl(-z~0^2 + fl(-z~1^2 + kappa2)) >= kappa2 (1 - 2u') - (z~0^2 + z~1^2)(1 + 2u'), u' = u(1 + u) (the squares
 //       are exact inside the FMAs).  With S = (1 - t)^2 (1 - 2^-22) log2(e) and
 //           kappa2 (1 - 2^-22) >= 1.000001 log2(e) [(ez_0^2 + ez_1^2) + hs delta^2]/t
 //       the chain gives  xe >= -A(d*) log2(e), i.e.  e = ex2(xe) >= exp(-A(d*))  (xe may exceed 0 by at most kappa2: e is then
@@ -442,7 +442,7 @@ __device__ __forceinline__ float screen_point(const ScreenCtx& m, const float2 p
   const float l10 = lds_f1_128(ra);
   const float2 zz = __ffma2_rn(make_float2(l.x, l.y), df, make_float2(l.z, l.w));  // l00 df0 + c0, l11 df1 + c1 (= z1)
   const float z0 = fmaf(l10, df.y, zz.x);
-  const float xe = fmaf(-zz.y, zz.y, fmaf(-z0, z0, m.kappa2));
+  const float xe = fmaf(-z0, z0, fmaf(-zz.y, zz.y, m.kappa2));  // z1's square first: it does not wait for l10
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xe));                       // 2 ulp, results below 2^-126 flushed: covered by the total's slack
   edge = fmaxf(fmaxf(edge, fabsf(df.x)), fabsf(df.y));

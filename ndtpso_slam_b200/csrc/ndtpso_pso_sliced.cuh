@@ -36,6 +36,9 @@ enum {
 #ifndef NDTPSO_SCREEN_JB
 #define NDTPSO_SCREEN_JB 8  // candidates the screen takes at a time first (more loads in flight, fewer reductions), then 4, then pairs
 #endif
+#ifndef NDTPSO_SCREEN_DEFER
+#define NDTPSO_SCREEN_DEFER 1  // the screen reduces a batch's sums while the next batch is being evaluated (2.178 -> 2.171 ms per 256 matches)
+#endif
 #ifndef NDTPSO_PROD_VARIANT
 #define NDTPSO_PROD_VARIANT 4
 #endif
@@ -527,12 +530,49 @@ __device__ __forceinline__ void screen_batch(const ScreenCtx& m, const ScreenPts
   if (packed_writer<JB>(lane) && (FULL || jj < hi)) lbpart[jj * NW + warp] = tot;
 }
 
+// the per-lane sums of a full batch of JB candidates (no reduction)
+template <int NPT, int JB>
+__device__ __forceinline__ void screen_batch_acc(const ScreenCtx& m, const ScreenPts<NPT>& p, const float4* pose32, int j, float (&acc)[JB]) {
+#pragma unroll
+  for (int b = 0; b < JB; ++b) {
+    const float4 ps = pose32[j + b];
+    const float2 tuv = make_float2(ps.x, ps.y), cs = make_float2(ps.z, ps.z), sc = make_float2(ps.w, ps.w);
+    float edge = 0.f;
+    acc[b] = screen_point(m, p.px2[0], p.py2[0], tuv, cs, sc, edge) * p.w[0];
+#pragma unroll
+    for (int k = 1; k < NPT; ++k) acc[b] = fmaf(screen_point(m, p.px2[k], p.py2[k], tuv, cs, sc, edge), p.w[k], acc[b]);
+    acc[b] = fmaf(edge > m.beta_c ? 1.f : 0.f, p.wsum, acc[b]);
+  }
+}
+
 // the screen over candidates [lo, hi): NDTPSO_SCREEN_JB at a time, then the rest in pairs
 template <int NPT>
 __device__ __forceinline__ void screen_candidates(const ScreenCtx& m, const ScreenPts<NPT>& p, const float4* pose32, float* lbpart, int lo, int hi,
                                                   int NW, int warp, int lane) {
   int j = lo;
+#if NDTPSO_SCREEN_DEFER
+  // the warp reduction of a batch (a chain of shuffles with no load in flight) is deferred by one batch, so that it overlaps
+  // the next batch's evaluations
+  constexpr int JB = NDTPSO_SCREEN_JB;
+  if (j + JB <= hi) {
+    float prev[JB];
+    screen_batch_acc<NPT, JB>(m, p, pose32, j, prev);
+    int jp = j;
+    for (j += JB; j + JB <= hi; j += JB) {
+      float acc[JB];
+      screen_batch_acc<NPT, JB>(m, p, pose32, j, acc);
+      const float tot = packed_warp_sum_f<JB>(prev, lane);
+      if (packed_writer<JB>(lane)) lbpart[(jp + packed_slot<JB>(lane)) * NW + warp] = tot;
+#pragma unroll
+      for (int b = 0; b < JB; ++b) prev[b] = acc[b];
+      jp = j;
+    }
+    const float tot = packed_warp_sum_f<JB>(prev, lane);
+    if (packed_writer<JB>(lane)) lbpart[(jp + packed_slot<JB>(lane)) * NW + warp] = tot;
+  }
+#else
   for (; j + NDTPSO_SCREEN_JB <= hi; j += NDTPSO_SCREEN_JB) screen_batch<NPT, NDTPSO_SCREEN_JB, true>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
+#endif
 #if NDTPSO_SCREEN_JB > 4
   for (; j + 4 <= hi; j += 4) screen_batch<NPT, 4, true>(m, p, pose32, lbpart, j, hi, NW, warp, lane);
 #endif

@@ -96,3 +96,27 @@ def test_bound_below_fp64_cost_on_golden_tables(golden, oracle, case):
     # exponents; this restatement also counts every point in the edge band on top of its term)
     conv = slice(0, 40)
     assert np.median((cost[conv] - lower[conv]) / np.abs(cost[conv])) < 0.05
+
+
+@pytest.mark.parametrize("geom", [(50.0, 0.5), (20.0, 0.25), (50.0, 2.0), (100.0, 1.0)])
+def test_bound_on_random_tables_with_needles(oracle, geom):
+    """The soak test's random tables (inverse covariances over 7.6 decades in one map, correlations up to 0.9999, means on cell
+    corners, points on cell edges and on the frame's border): some records need more than the table's kappa2 gives and take the
+    trivial bound; the restated bound must still never exceed the oracle's cost."""
+    from tests.test_gpu_screen_soak import pose_sets, random_problem
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        flat, centre = random_problem(rng, geom[0], geom[1], 500)
+        n = flat["w_cells"] * flat["h_cells"]
+        dense = dict(flat)
+        dense["mean"] = np.zeros((n, 2))
+        dense["inv_cov"] = np.zeros((n, 4))
+        dense["built"] = np.zeros(n, dtype=np.uint8)
+        dense["mean"][flat["cell_index"]] = flat["mean"]
+        dense["inv_cov"][flat["cell_index"]] = flat["inv_cov"]
+        dense["built"][flat["cell_index"]] = 1
+        poses = pose_sets(rng, centre, flat["width_m"], 64)
+        poses = poses[np.abs(poses[:, :2]).max(axis=1) < 1e4]  # the kernel's host side admits (pmax + W)/cs <= 2^22 only
+        lower = screen_bound(flat, poses)
+        cost = oracle.cost_many(dense, poses)
+        assert (lower <= cost).all(), (geom, np.argwhere(lower > cost)[:3], lower[lower > cost][:3], cost[lower > cost][:3])
